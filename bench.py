@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — frustums/s forward of the B200 frustum hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload car|people|sunrgbd] [--batch 32] [--precision 0|1]
+
+One "step" = one forward of the hot path (grouping -> PointNet -> FCN -> heads/decode) over one
+batch of `--batch` synthetic frustums per GPU (default: cfgs/det_sample.yaml car, B=32 x 1024
+points = BASELINE.json configs[1]).  Weak scaling: every rank processes its own B frustums;
+for N>1 the per-rank result block is all-gathered over NCCL inside the timed region (the only
+exchange of the inference path).
+
+Printed JSON (rank 0, one line): the base contract keys plus `roofline`, `cpu_baseline`,
+`e2e`, `clocks`, `gpu_launches`, `hbm` (see DESIGN.md "Measurement").
+`--impl reference` times the reference's own PyTorch path on the host CPUs (the oracle port:
+/root/reference cannot travel to the GPU box and its CUDA op no longer compiles).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frustums/sec fwd"
+UNIT = "frustums/s"
+
+# Algorithmic per-frustum figures
+ALGO = {
+    "car": dict(bytes=32.0e3, gflop=2.977),
+    "people": dict(bytes=61.7e3, gflop=7.469),
+    "sunrgbd": dict(bytes=31.5e3, gflop=2.526),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234):
+    """frustums/s of the reference algorithm on host CPUs (oracle port, all host threads)."""
+    import torch
+    from frustum_convnet_b200 import config, synth
+    from oracle import model as om
+    cfg, w = config.load_workload(workload)
+    n = host_threads()
+    torch.set_num_threads(n)
+    sd = om.to_torch_state(synth.make_state_dict(w["arch"], w["num_vec"], cfg.DATA.DATASET_NAME, seed=7))
+    data = synth.make_frustums(workload, sample_B, seed=seed)
+    mean = config.DATASET_INFO[cfg.DATA.DATASET_NAME].MEAN_SIZE_ARRAY
+    run = lambda: om.pointnet_det_eval(data, sd, cfg.DATA.HEIGHT_HALF, w["arch"].nsample, mean)
+    for _ in range(warm):
+        run()
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    return sample_B / float(np.median(ts)), float(np.sum(ts)), n
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample_B = min(args.batch, 8)
+    t0 = time.perf_counter()
+    rate, busy, n = cpu_reference_rate(args.workload, sample_B, args.steps, max(args.warmup, 1))
+    ms = 1e3 * sample_B / rate
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s det_sample B=%d x N pts (reference arm: %d-frustum sample per step)" % (
+            args.workload, args.batch, sample_B), "batch_per_gpu": args.batch},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
+                         "sample": "%d steps x %d frustums, oracle port of models/det_base.py on torch CPU fp32"
+                                   % (args.steps, sample_B)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="car", choices=list(ALGO))
+    ap.add_argument("--batch", type=int, default=32, help="frustums per GPU per step")
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("FCN_PRECISION", "0")))
+    ap.add_argument("--pool-mb", type=float, default=160.0, help="distinct input pool size (> L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from frustum_convnet_b200 import config, synth
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, w = config.load_workload(args.workload)
+    modname = "det_base_sunrgbd" if w["arch"].num_scales == 5 else "det_base"
+    mod = __import__("frustum_convnet_b200." + modname, fromlist=["PointNetDet"])
+    sd = synth.make_state_dict(w["arch"], w["num_vec"], cfg.DATA.DATASET_NAME, seed=7)
+    model = mod.PointNetDet(3, num_vec=w["num_vec"])
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model.precision = args.precision
+    model = model.to(dev).eval()
+    model.use_cuda_graph = True
+    B, S = args.batch, w["arch"].num_scales
+
+    # ---- input pool larger than L2 (126 MB): distinct batches cycled through the timed loop
+    one = synth.make_frustums(args.workload, B, seed=1234 + rank)
+    keys = ["point_cloud"] + ["center_ref%d" % (i + 1) for i in range(S)] + ["one_hot"]
+    step_in_bytes = int(sum(one[k].nbytes for k in keys))
+    npool = max(2, int(np.ceil(args.pool_mb * 1e6 / step_in_bytes)))
+    ngen = min(npool, 8)   # 8 seeded batches, the rest are per-frustum rotations of them
+    base = [synth.make_frustums(args.workload, B, seed=1234 + rank + 1000 * i) for i in range(ngen)]
+    host_pool, dev_pool = [], []
+    for i in range(npool):
+        src = base[i % ngen]
+        sh = (i // ngen) % B
+        hb = {k: torch.from_numpy(np.roll(src[k], sh, axis=0).copy()).pin_memory() for k in keys}
+        host_pool.append(hb)
+        dev_pool.append({k: v.to(dev) for k, v in hb.items()})
+    T = [one["center_ref%d" % (i + 1)].shape[2] for i in range(S)]
+
+    def step_resident(i):
+        out = model(dev_pool[i % npool])
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, plan.out_flat)
+        return out
+
+    eng = model.engine()
+    plan = eng.plan(B, one["point_cloud"].shape[2], T)
+    if world > 1:
+        gather_buf = torch.empty((world,) + tuple(plan.out_flat.shape), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: inputs resident in HBM
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(args.warmup + i)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- e2e: public API with HOST (pinned) buffers, H2D + D2H inside the timed region
+    host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in plan.out]
+    d2h_bytes = int(sum(o.numel() * 4 for o in host_out))
+
+    def step_e2e(i):
+        hb = host_pool[i % npool]
+        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        out = model(db)
+        for h, o in zip(host_out, out):
+            h.copy_(o, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf, plan.out_flat)
+
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(t.item()) / args.steps * 1e-3)
+
+    # ---- per-kernel timing of the eager launch sequence (CUDA events on the launching stream)
+    kt = plan.time_kernels(dev_pool, iters=20) if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    algo = ALGO[args.workload]
+    dom = max(kt["kernels"], key=lambda k: k["ms"])
+    tf32_peak = peaks["bf16_tflops"] / 2.0   # kind::tf32 runs at half the bf16 rate; burst figure (kernel timed alone)
+    roofline = {
+        "bound": "tensor", "kernel": dom["name"], "achieved": dom["executed_tflops"], "peak": tf32_peak,
+        "unit": "TFLOP/s", "frac": dom["executed_tflops"] / tf32_peak,
+        "peak_source": "MEASURED_PEAKS.json bf16_tflops/2 (%s)" % peaks["source"],
+        "ms_per_launch": dom["ms"], "executed_gflop_per_launch": dom["executed_gflop"],
+        "nominal_gflop_per_launch": dom["nominal_gflop"], "traffic": None,
+        "precision": "tf32-tcgen05" if args.precision == 1 else "fp32-simt",
+    }
+    hbm = {"achieved": value * algo["bytes"] / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+           "frac": value * algo["bytes"] / 1e9 / peaks["hbm_gbs"],
+           "algorithmic_bytes_per_frustum": algo["bytes"],
+           "note": "path is compute-bound by design (SURVEY.md 8(d)); HBM fraction is expected to be small"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32" if args.precision == 1 else "f32", "data": "synthetic",
+        "config": {"workload": "%s cfgs/%s B=%d frustums/GPU x %d pts, T=%s, forward (eval)" % (
+            args.workload, w["yaml"], B, one["point_cloud"].shape[2], T),
+            "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "l2": "inputs cycle through a %d-batch pool (%.0f MB > 126 MB L2); weights/workspaces stay L2-resident"
+                  % (npool, npool * step_in_bytes / 1e6),
+            "cuda_graph": True, "precision": roofline["precision"]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step_in_bytes,
+                "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": kt["launches_per_step"] * args.steps,
+        "launches_per_step": kt["launches_per_step"],
+        "roofline": roofline, "hbm": hbm, "clocks": clocks,
+        "achieved_tflops_nominal": value * algo["gflop"] / 1e3,
+        "kernel_ms": {k["name"]: round(k["ms"], 5) for k in kt["kernels"]},
+        "unique_row_fraction": kt["unique_row_fraction"],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sample_B = min(B, 8)
+        rate, busy, n = cpu_reference_rate(args.workload, sample_B, iters=5, warm=1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
+                                "sample": "5 forwards of %d frustums (%.1f s of CPU work), oracle port on torch CPU fp32"
+                                          % (sample_B, busy)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""ctypes binding of libfrustum_b200.so (the C ABI declared in include/frustum_b200.h).
+
+No CPU fallback: if the shared library is missing this module raises at load time, and every
+entry point raises ``RuntimeError`` with ``fcn_last_error()`` on a non-zero status, mirroring
+the reference where AT_ASSERTM / THCudaCheck surface as Python exceptions
+(/root/reference/ops/query_depth_point/query_depth_point_cuda.cpp:5-10, ..._kernel.cu:85).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_SCALES = 8
+MAX_SEGS = 4
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfrustum_b200.so")
+
+
+class GroupArgs(C.Structure):
+    _fields_ = [
+        ("num_scales", C.c_int), ("B", C.c_int), ("N", C.c_int), ("num_vec", C.c_int),
+        ("tile_rows", C.c_int), ("unique_rows", C.c_int),
+        ("pc", C.c_void_p), ("one_hot", C.c_void_p),
+        ("centers", C.c_void_p * MAX_SCALES),
+        ("T", C.c_int * MAX_SCALES), ("K", C.c_int * MAX_SCALES),
+        ("dis_z", C.c_float * MAX_SCALES),
+        ("c3", C.c_int * MAX_SCALES), ("ld_feat", C.c_int * MAX_SCALES),
+        ("row_cap", C.c_int * MAX_SCALES), ("tile_cap", C.c_int * MAX_SCALES),
+        ("rows", C.c_void_p * MAX_SCALES), ("cnt", C.c_void_p * MAX_SCALES),
+        ("feat", C.c_void_p * MAX_SCALES), ("tiles", C.c_void_p * MAX_SCALES),
+        ("ntiles", C.c_void_p),
+    ]
+
+
+class PointnetArgs(C.Structure):
+    _fields_ = [
+        ("C1", C.c_int), ("C2", C.c_int), ("C3", C.c_int), ("T", C.c_int), ("K", C.c_int),
+        ("ld_feat", C.c_int), ("row_cap", C.c_int), ("tile_rows", C.c_int),
+        ("unpooled", C.c_int), ("precision", C.c_int), ("B", C.c_int),
+        ("rows", C.c_void_p), ("tiles", C.c_void_p), ("ntiles", C.c_void_p),
+        ("max_tiles", C.c_int),
+        ("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
+        ("w3t", C.c_void_p), ("b3", C.c_void_p),
+        ("w2_tc", C.c_void_p), ("w3_tc", C.c_void_p),
+        ("out", C.c_void_p),
+    ]
+
+
+class ConvSeg(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("ld", C.c_int), ("C", C.c_int), ("T_src", C.c_int),
+                ("tap", C.c_int), ("stride", C.c_int)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("T_out", C.c_int), ("n_seg", C.c_int),
+        ("seg", ConvSeg * MAX_SEGS),
+        ("K_pad", C.c_int), ("n_cols", C.c_int), ("Cout", C.c_int), ("up", C.c_int),
+        ("relu", C.c_int), ("precision", C.c_int),
+        ("wt", C.c_void_p), ("bias", C.c_void_p), ("w_tc", C.c_void_p),
+        ("out", C.c_void_p),
+        ("ld_out", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
+_I, _F, _P = C.c_int, C.c_float, C.c_void_p
+SIGNATURES = {
+    "fcn_version": (_I, []),
+    "fcn_last_error": (C.c_char_p, []),
+    "fcn_query_depth_point_bn3": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+    "fcn_query_depth_point_b3n": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+    "fcn_group_rows": (_I, [C.POINTER(GroupArgs), _P]),
+    "fcn_pointnet_tiles": (_I, [C.POINTER(PointnetArgs), _P]),
+    "fcn_conv_gemm": (_I, [C.POINTER(ConvArgs), _P]),
+    "fcn_decode_eval": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fcn_bct_to_btc": (_I, [_I, _I, _I, _I, _P, _P, _P]),
+    "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libfrustum_b200.so is missing (%s). Build it with "
+                "`python -m frustum_convnet_b200.build` (or __graft_entry__.build()); there is no "
+                "CPU or PyTorch fallback for the frustum hot path." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().fcn_last_error().decode(errors="replace")
+        raise RuntimeError("libfrustum_b200 %s failed (%d): %s" % (what, status, msg))
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

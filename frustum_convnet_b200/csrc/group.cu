@@ -1,0 +1,286 @@
+// Sliding-frustum grouping kernels.
+//
+//  * qdp_kernel        — drop-in for query_depth_point_gpu
+//                        (/root/reference/ops/query_depth_point/query_depth_point_cuda_kernel.cu:16-65):
+//                        one WARP per (frustum, section) instead of one thread; 32 points are tested
+//                        per step with ballot/popc compaction, so idx stores are contiguous and the
+//                        z reads are coalesced.  Bit-exact: same fp32 `fabsf(z2 - z1) < dis_z`
+//                        predicate, same first-K-in-index-order selection, same back-fill.
+//  * group_rows_kernel — fused form used by the PointNet tile kernels: no int64 idx tensor is
+//                        materialised; each section emits float4 {x-cx, y-cy, z-cz, t} row records
+//                        (gather + centre subtraction of models/det_base.py:75-80 folded in).
+#include "common.cuh"
+
+namespace fcn {
+
+thread_local char g_err[512] = "";
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// The predicate of cu:48-53.  __fsub_rn / fabsf keep it a plain IEEE fp32 subtract (no contraction).
+__device__ __forceinline__ bool depth_hit(float zc, float zp, float dis_z) {
+    return fabsf(__fsub_rn(zc, zp)) < dis_z;
+}
+
+constexpr int QDP_WARPS = 8;
+
+template <bool CHANNEL_FIRST>
+__global__ void __launch_bounds__(QDP_WARPS * 32)
+qdp_kernel(int n, int m, float dis_z, int nsample, const float *__restrict__ xyz1,
+           const float *__restrict__ xyz2, long long *__restrict__ idx, int *__restrict__ pts_cnt) {
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sec = blockIdx.x * QDP_WARPS + warp;
+    if (sec >= m) return;
+    const float *z1;
+    int zstride;
+    float zc;
+    if (CHANNEL_FIRST) {
+        z1 = xyz1 + (size_t)b * 3 * n + 2 * (size_t)n;
+        zstride = 1;
+        zc = __ldg(xyz2 + (size_t)b * 3 * m + 2 * (size_t)m + sec);
+    } else {
+        z1 = xyz1 + (size_t)b * n * 3 + 2;
+        zstride = 3;
+        zc = __ldg(xyz2 + ((size_t)b * m + sec) * 3 + 2);
+    }
+    long long *out = idx + ((size_t)b * m + sec) * nsample;
+    int cnt = 0, first = 0;
+    for (int base = 0; base < n && cnt < nsample; base += 32) {
+        const int k = base + lane;
+        bool hit = false;
+        if (k < n) hit = depth_hit(zc, __ldg(z1 + (size_t)k * zstride), dis_z);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+            if (cnt == 0) first = base + __ffs(mask) - 1;
+            const int pos = cnt + __popc(mask & ((1u << lane) - 1));
+            if (hit && pos < nsample) out[pos] = k;
+            cnt += __popc(mask);
+        }
+    }
+    cnt = min(cnt, nsample);
+    // back-fill (cu:55-59): slots >= cnt repeat the first hit; empty sections stay all-zero
+    for (int l = cnt + lane; l < nsample; l += 32) out[l] = first;
+    if (lane == 0) pts_cnt[(size_t)b * m + sec] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct GroupParams {
+    fcn_group_args a;
+};
+
+constexpr int GROUP_THREADS = 512;
+
+__global__ void __launch_bounds__(GROUP_THREADS)
+group_rows_kernel(const __grid_constant__ GroupParams P) {
+    extern __shared__ float smem[];
+    const fcn_group_args &a = P.a;
+    const int b = blockIdx.x, s = blockIdx.y;
+    const int N = a.N, T = a.T[s], K = a.K[s];
+    const float dis_z = a.dis_z[s];
+    float *sx = smem, *sy = sx + N, *sz = sy + N;
+    float *cz = sz + N;                      // T
+    int *scnt = (int *)(cz + T);             // T
+    int *sstart = scnt + T;                  // T
+    __shared__ int s_warp_tot[GROUP_THREADS / 32];
+    __shared__ int s_carry, s_total, s_tile_base;
+
+    const float *pc = a.pc + (size_t)b * 3 * N;
+    const float *cen = a.centers[s] + (size_t)b * 3 * T;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        sx[i] = __ldg(pc + i);
+        sy[i] = __ldg(pc + N + i);
+        sz[i] = __ldg(pc + 2 * N + i);
+    }
+    for (int i = threadIdx.x; i < T; i += blockDim.x) cz[i] = __ldg(cen + 2 * T + i);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    // pass 1: hit counts (capped at K)
+    for (int t = warp; t < T; t += nwarp) {
+        const float zc = cz[t];
+        int cnt = 0;
+        for (int base = 0; base < N && cnt < K; base += 32) {
+            const int k = base + lane;
+            const bool hit = (k < N) && depth_hit(zc, sz[k], dis_z);
+            cnt += __popc(__ballot_sync(0xffffffffu, hit));
+        }
+        if (lane == 0) scnt[t] = min(cnt, K);
+    }
+    __syncthreads();
+    // exclusive scan of rows-per-section over T (chunks of blockDim with a running carry)
+    const bool uniq = a.unique_rows != 0;
+    for (int base = 0; base < T; base += blockDim.x) {
+        const int t = base + threadIdx.x;
+        int v = 0;
+        if (t < T) v = uniq ? scnt[t] : K;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_warp_tot[w];
+        const int carry = s_carry;
+        if (t < T) sstart[t] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int total = s_carry;
+        s_total = total;
+        const int nt = ceil_div(total, a.tile_rows);
+        s_tile_base = nt > 0 ? atomicAdd(a.ntiles + s, nt) : 0;
+    }
+    __syncthreads();
+    const int total = s_total;
+    // tile table
+    {
+        int4 *tiles = (int4 *)a.tiles[s];
+        const int nt = ceil_div(total, a.tile_rows);
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+            const int row0 = i * a.tile_rows;
+            if (s_tile_base + i < a.tile_cap[s])
+                tiles[s_tile_base + i] = make_int4(b, row0, min(a.tile_rows, total - row0), 0);
+        }
+    }
+    // side outputs: cnt, zero-filled feature block + one-hot channels
+    {
+        int *gcnt = a.cnt[s] + (size_t)b * T;
+        for (int i = threadIdx.x; i < T; i += blockDim.x) gcnt[i] = scnt[i];
+        float *feat = a.feat[s];
+        if (feat != nullptr) {
+            const int ld = a.ld_feat[s], c3 = a.c3[s], V = a.num_vec;
+            float4 *f4 = (float4 *)(feat + (size_t)b * T * ld);
+            const int n4 = T * ld / 4;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) f4[i] = z4;
+            __syncthreads();
+            if (a.one_hot != nullptr) {
+                float *fb = feat + (size_t)b * T * ld;
+                for (int i = threadIdx.x; i < T * V; i += blockDim.x) {
+                    const int t = i / V, v = i - t * V;
+                    fb[(size_t)t * ld + c3 + v] = __ldg(a.one_hot + (size_t)b * V + v);
+                }
+            }
+        }
+    }
+    // pass 2: emit row records
+    float4 *rows = (float4 *)a.rows[s] + (size_t)b * a.row_cap[s];
+    const float *cx_g = cen, *cy_g = cen + T;
+    for (int t = warp; t < T; t += nwarp) {
+        const float zc = cz[t];
+        const float cx = __ldg(cx_g + t), cy = __ldg(cy_g + t);
+        const int c = scnt[t];
+        float4 *out = rows + sstart[t];
+        if (c == 0) {
+            if (!uniq) {  // masked section: K rows gathering point 0 (zero-initialised idx), flagged
+                const float4 r = make_float4(__fsub_rn(sx[0], cx), __fsub_rn(sy[0], cy),
+                                             __fsub_rn(sz[0], zc), __int_as_float(t | 0x80000000));
+                for (int l = lane; l < K; l += 32) out[l] = r;
+            }
+            continue;
+        }
+        int cnt = 0, first = 0;
+        for (int base = 0; base < N && cnt < K; base += 32) {
+            const int k = base + lane;
+            const bool hit = (k < N) && depth_hit(zc, sz[k], dis_z);
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (mask) {
+                if (cnt == 0) first = base + __ffs(mask) - 1;
+                const int pos = cnt + __popc(mask & ((1u << lane) - 1));
+                if (hit && pos < K)
+                    out[pos] = make_float4(__fsub_rn(sx[k], cx), __fsub_rn(sy[k], cy),
+                                           __fsub_rn(sz[k], zc), __int_as_float(t));
+                cnt += __popc(mask);
+            }
+        }
+        if (!uniq) {
+            const float4 r = make_float4(__fsub_rn(sx[first], cx), __fsub_rn(sy[first], cy),
+                                         __fsub_rn(sz[first], zc), __int_as_float(t));
+            for (int l = c + lane; l < K; l += 32) out[l] = r;
+        }
+    }
+}
+
+}  // namespace fcn
+
+using namespace fcn;
+
+extern "C" int fcn_version(void) { return 100; }
+extern "C" const char *fcn_last_error(void) { return fcn::g_err; }
+
+static int qdp_launch(bool channel_first, int b, int n, int m, float dis_z, int nsample,
+                      const float *xyz1, const float *xyz2, int64_t *idx, int32_t *pts_cnt,
+                      fcn_stream_t stream) {
+    FCN_REQUIRE(b >= 0 && n >= 0 && m >= 0, "negative size");
+    FCN_REQUIRE(nsample > 0, "nsample must be positive");
+    FCN_REQUIRE(b <= 65535, "batch exceeds gridDim.y");
+    if (b == 0 || m == 0) return FCN_OK;
+    FCN_REQUIRE(xyz1 || n == 0, "xyz1 is NULL");
+    FCN_REQUIRE(xyz2 && idx && pts_cnt, "NULL pointer");
+    dim3 grid(ceil_div(m, QDP_WARPS), b), block(QDP_WARPS * 32);
+    if (channel_first)
+        qdp_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(
+            n, m, dis_z, nsample, xyz1, xyz2, (long long *)idx, pts_cnt);
+    else
+        qdp_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(
+            n, m, dis_z, nsample, xyz1, xyz2, (long long *)idx, pts_cnt);
+    FCN_LAUNCH_CHECK();
+    return FCN_OK;
+}
+
+extern "C" int fcn_query_depth_point_bn3(int b, int n, int m, float dis_z, int nsample,
+                                         const float *xyz1, const float *xyz2, int64_t *idx,
+                                         int32_t *pts_cnt, fcn_stream_t stream) {
+    return qdp_launch(false, b, n, m, dis_z, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+}
+extern "C" int fcn_query_depth_point_b3n(int b, int n, int m, float dis_z, int nsample,
+                                         const float *xyz1, const float *xyz2, int64_t *idx,
+                                         int32_t *pts_cnt, fcn_stream_t stream) {
+    return qdp_launch(true, b, n, m, dis_z, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+}
+
+extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
+    FCN_REQUIRE(args != nullptr, "args is NULL");
+    const fcn_group_args &a = *args;
+    FCN_REQUIRE(a.num_scales >= 1 && a.num_scales <= FCN_MAX_SCALES, "num_scales out of range");
+    FCN_REQUIRE(a.B >= 0 && a.N >= 1, "bad B/N");
+    FCN_REQUIRE(a.tile_rows >= 1, "tile_rows must be positive");
+    FCN_REQUIRE(a.pc && a.ntiles, "NULL pointer");
+    if (a.B == 0) return FCN_OK;
+    int maxT = 0;
+    for (int s = 0; s < a.num_scales; ++s) {
+        FCN_REQUIRE(a.T[s] >= 1 && a.K[s] >= 1, "bad T/K");
+        FCN_REQUIRE(a.centers[s] && a.rows[s] && a.cnt[s] && a.tiles[s], "NULL per-scale pointer");
+        FCN_REQUIRE(a.row_cap[s] >= a.T[s] * a.K[s], "row_cap too small");
+        FCN_REQUIRE(a.feat[s] == nullptr || a.ld_feat[s] % 4 == 0, "ld_feat must be a multiple of 4");
+        FCN_REQUIRE(a.feat[s] == nullptr || a.ld_feat[s] >= a.c3[s] + a.num_vec, "ld_feat too small");
+        maxT = a.T[s] > maxT ? a.T[s] : maxT;
+    }
+    const size_t smem = sizeof(float) * (3 * (size_t)a.N + 3 * (size_t)maxT);
+    FCN_REQUIRE(smem <= 200 * 1024, "N/T too large for the shared-memory staging");
+    GroupParams P;
+    P.a = a;
+    if (smem > 48 * 1024)
+        FCN_CUDA(cudaFuncSetAttribute(group_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    dim3 grid(a.B, a.num_scales);
+    group_rows_kernel<<<grid, GROUP_THREADS, smem, (cudaStream_t)stream>>>(P);
+    FCN_LAUNCH_CHECK();
+    return FCN_OK;
+}

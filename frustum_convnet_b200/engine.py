@@ -1,0 +1,497 @@
+"""Host-side engine of the B200 frustum hot path (eval / inference).
+
+Owns (as torch tensors — the library itself allocates nothing, SURVEY.md section 8(b) "Ownership"):
+  * the BN-folded, kernel-ready weight pack built from a reference-format state dict
+    (BN folding happens here at eval()/load time, never inside the state dict);
+  * per-shape workspaces (row records, tile tables, position-major activations, outputs);
+  * an optional CUDA graph of the whole forward (no host sync exists on the path: the
+    `indices.max()/min()` assert of /root/reference/models/det_base.py:70 is dropped because the
+    kernels emit in-range indices by construction).
+
+The sequence of C-ABI calls mirrors PointNetDet.forward (det_base.py:334-412):
+  fcn_group_rows            QueryDepthPoint + gather + centre subtraction, all scales  (:68-80)
+  fcn_pointnet_tiles  x S   conv1..3 + BN + ReLU + mask + max over K                  (:95-101,134-143)
+  fcn_conv_gemm       x 14  ConvFeatNet + heads (cat == extra K segments)             (:196-224,367-368)
+  fcn_decode_eval           softmax / argmax / box decode                             (:376-411)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import DATASET_INFO, ArchSpec
+from .synth import fcn_layer_table, reg_out_size
+
+BN_EPS = 1e-5
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _fold_bn(sd, prefix) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(scale, shift) in float64 of an eval-mode BatchNorm (models/common.py:38-63 factories)."""
+    g = sd[prefix + ".weight"].double()
+    b = sd[prefix + ".bias"].double()
+    m = sd[prefix + ".running_mean"].double()
+    v = sd[prefix + ".running_var"].double()
+    s = g / torch.sqrt(v + BN_EPS)
+    return s, b - m * s
+
+
+class _ConvLayer:
+    """One fcn_conv_gemm call: packed weights + symbolic segment/output description."""
+
+    def __init__(self, name, segs, K_pad, n_cols, Cout, up, relu, wt, bias, out, c_off):
+        self.name, self.segs, self.K_pad, self.n_cols = name, segs, K_pad, n_cols
+        self.Cout, self.up, self.relu, self.wt, self.bias = Cout, up, relu, wt, bias
+        self.out, self.c_off = out, c_off
+
+
+class FrustumEngine:
+    """Kernel-ready form of one PointNetDet (KITTI 4-scale or SUN-RGBD 5-scale)."""
+
+    def __init__(self, arch: ArchSpec, num_vec: int, dataset: str, dists: Sequence[float],
+                 num_bins: int, state_dict: Dict[str, torch.Tensor], device, precision: int = 0):
+        self.arch, self.num_vec, self.dataset = arch, int(num_vec), dataset
+        self.dists = [float(d) for d in dists]
+        assert len(self.dists) == arch.num_scales
+        self.num_bins = int(num_bins)
+        self.num_size = DATASET_INFO[dataset].NUM_SIZE_CLUSTER
+        self.device = torch.device(device)
+        self.precision = int(precision)
+        self.tile_rows = 64 if self.precision == 0 else 128
+        self.out_size = reg_out_size(dataset, self.num_bins)
+        self.ld_logit = _round_up(2 + self.out_size, 64)
+        self.c3 = [m[2] for m in arch.mlps]
+        self.ld_feat = [_round_up(c + self.num_vec, 4) for c in self.c3]
+        self.mean_size = torch.tensor(DATASET_INFO[dataset].MEAN_SIZE_ARRAY, dtype=torch.float32,
+                                      device=self.device)
+        self._plans: Dict[tuple, "_Plan"] = {}
+        self.pack(state_dict)
+
+    # ------------------------------------------------------------------ weight packing
+    def pack(self, state_dict: Dict[str, torch.Tensor]):
+        sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
+        dev, f32 = self.device, torch.float32
+        self.pn = []
+        self.layers: List[_ConvLayer] = []
+        self._plans.clear()
+        self.has_feat = "feat_net.pointnet1.conv1.0.weight" in sd
+        self.has_fcn = "conv_net.block1_conv1.0.weight" in sd
+        self.has_heads = "cls_out.weight" in sd
+        for i, (c1, c2, c3) in enumerate(self.arch.mlps if self.has_feat else ()):
+            p = "feat_net.pointnet%d" % (i + 1)
+            lay = {}
+            for j in (1, 2, 3):
+                w = sd["%s.conv%d.0.weight" % (p, j)].double()[:, :, 0, 0]      # (Co,Ci)
+                s, sh = _fold_bn(sd, "%s.conv%d.1" % (p, j))
+                lay["w%dt" % j] = (w * s[:, None]).t().contiguous().to(f32)     # (Ci,Co)
+                lay["b%d" % j] = sh.to(f32).contiguous()
+            self.pn.append(lay)
+        S, V = self.arch.num_scales, self.num_vec
+        widths = (128, 256, 512, 512)[: S - 1]
+        if not self.has_fcn:
+            return
+
+        def padded(c):
+            return _round_up(c, 32)
+
+        def conv3(name, src, ci, co, stride, out):
+            w = sd["conv_net.%s.0.weight" % name].double()                      # (Co,Ci,3)
+            s, sh = _fold_bn(sd, "conv_net.%s.1" % name)
+            cp, ncols = padded(ci), _round_up(co, 64)
+            wt = torch.zeros(3 * cp, ncols, dtype=torch.float64, device=dev)
+            for j in range(3):
+                wt[j * cp: j * cp + ci, :co] = (w[:, :, j] * s[:, None]).t()
+            bias = torch.zeros(ncols, dtype=torch.float64, device=dev)
+            bias[:co] = sh
+            segs = [(src, ci, j - 1, stride) for j in range(3)]
+            self.layers.append(_ConvLayer(name, segs, 3 * cp, ncols, co, 1, 1, wt.to(f32).contiguous(),
+                                          bias.to(f32).contiguous(), out, 0))
+
+        def merge(name, src_a, ca, src_b, cb, co, out):
+            w = sd["conv_net.%s.0.weight" % name].double()[:, :, 0]            # (Co, ca+cb)
+            s, sh = _fold_bn(sd, "conv_net.%s.1" % name)
+            pa, pb, ncols = padded(ca), padded(cb), _round_up(co, 64)
+            wt = torch.zeros(pa + pb, ncols, dtype=torch.float64, device=dev)
+            wt[:ca, :co] = (w[:, :ca] * s[:, None]).t()
+            wt[pa: pa + cb, :co] = (w[:, ca:] * s[:, None]).t()
+            bias = torch.zeros(ncols, dtype=torch.float64, device=dev)
+            bias[:co] = sh
+            segs = [(src_a, ca, 0, 1), (src_b, cb, 0, 1)]
+            self.layers.append(_ConvLayer(name, segs, pa + pb, ncols, co, 1, 1, wt.to(f32).contiguous(),
+                                          bias.to(f32).contiguous(), out, 0))
+
+        def deconv(name, src, ci, co, k, c_off):
+            w = sd["conv_net.%s.0.weight" % name].double()                      # (Ci,Co,k)
+            s, sh = _fold_bn(sd, "conv_net.%s.1" % name)
+            ncols = _round_up(k * co, 64)
+            wt = torch.zeros(padded(ci), ncols, dtype=torch.float64, device=dev)
+            bias = torch.zeros(ncols, dtype=torch.float64, device=dev)
+            for j in range(k):
+                wt[:ci, j * co:(j + 1) * co] = w[:, :, j] * s[None, :]
+                bias[j * co:(j + 1) * co] = sh
+            self.layers.append(_ConvLayer(name, [(src, ci, 0, 1)], padded(ci), ncols, co, k, 1,
+                                          wt.to(f32).contiguous(), bias.to(f32).contiguous(), "cat", c_off))
+
+        conv3("block1_conv1", "feat1", self.c3[0] + V, self.arch.block1_out, 1, "x1")
+        prev, prev_c = "x1", self.arch.block1_out
+        for i in range(2, S + 1):
+            w = widths[i - 2]
+            conv3("block%d_conv1" % i, prev, prev_c, w, 2, "a%d" % i)
+            conv3("block%d_conv2" % i, "a%d" % i, w, w, 1, "b%d" % i)
+            merge("block%d_merge" % i, "b%d" % i, w, "feat%d" % i, self.c3[i - 1] + V, w, "m%d" % i)
+            prev, prev_c = "m%d" % i, w
+        for i in range(2, S + 1):
+            deconv("block%d_deconv" % i, "m%d" % i, widths[i - 2], 256, 2 ** (i - 2), 256 * (i - 2))
+        if not self.has_heads:
+            return
+        # heads: columns [cls0, cls1, reg...] zero-padded to ld_logit (det_base.py:250-251,367-368)
+        cin = self.arch.reg_in
+        wt = torch.zeros(_round_up(cin, 32), self.ld_logit, dtype=torch.float32, device=dev)
+        bias = torch.zeros(self.ld_logit, dtype=torch.float32, device=dev)
+        wt[:cin, 0:2] = sd["cls_out.weight"][:, :, 0].t()
+        wt[:cin, 2:2 + self.out_size] = sd["reg_out.weight"][:, :, 0].t()
+        bias[0:2] = sd["cls_out.bias"]
+        bias[2:2 + self.out_size] = sd["reg_out.bias"]
+        self.layers.append(_ConvLayer("heads", [("cat", cin, 0, 1)], _round_up(cin, 32), self.ld_logit,
+                                      self.ld_logit, 1, 0, wt.contiguous(), bias.contiguous(), "logits", 0))
+
+    # ------------------------------------------------------------------ shape plans
+    def plan(self, B: int, N: int, T: Sequence[int]) -> "_Plan":
+        key = (int(B), int(N), tuple(int(t) for t in T))
+        p = self._plans.get(key)
+        if p is None:
+            p = _Plan(self, *key)
+            self._plans[key] = p
+        return p
+
+    # ------------------------------------------------------------------ public calls
+    @torch.no_grad()
+    def forward(self, pc: torch.Tensor, centers: Sequence[torch.Tensor], one_hot, use_graph=False):
+        """Eval forward -> the 6-tuple of det_base.py:411."""
+        p = self.plan(pc.shape[0], pc.shape[2], [c.shape[2] for c in centers])
+        return p.run(pc, centers, one_hot, use_graph=use_graph)
+
+    @torch.no_grad()
+    def pointnet_feat(self, pc, centers, one_hot):
+        """API #3: PointNetFeat.forward -> tuple of channel-first (B, C3+V, T_i)."""
+        p = self.plan(pc.shape[0], pc.shape[2], [c.shape[2] for c in centers])
+        return p.run_feat(pc, centers, one_hot)
+
+    @torch.no_grad()
+    def conv_feat_net(self, feats_bct: Sequence[torch.Tensor]):
+        """ConvFeatNet.forward on channel-first inputs -> (B, 256*(S-1), T2)."""
+        B = feats_bct[0].shape[0]
+        p = self.plan(B, 1, [f.shape[2] for f in feats_bct])
+        return p.run_fcn_bct(feats_bct)
+
+    @torch.no_grad()
+    def pointnet_module(self, scale: int, pc, new_pc):
+        """API #2: PointNetModule.forward -> masked, un-pooled (B, C3, T, K)."""
+        return _run_module(self, scale, pc, new_pc)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Plan:
+    """Workspace + prebuilt C argument structs for one (B, N, T...) shape."""
+
+    def __init__(self, eng: FrustumEngine, B: int, N: int, T: Tuple[int, ...]):
+        self.eng, self.B, self.N, self.T = eng, B, N, T
+        arch, dev = eng.arch, eng.device
+        S = arch.num_scales
+        assert len(T) == S, "expected %d section lists, got %d" % (S, len(T))
+        for i in range(1, S):  # FCN length bookkeeping (k3 s2 p1): T_i == ceil(T_{i-1}/2)
+            assert T[i] == (T[i - 1] + 1) // 2, \
+                "section counts %s are not a /2 pyramid (ConvFeatNet cat would fail)" % (T,)
+        f32 = torch.float32
+        K = arch.nsample
+        tr = eng.tile_rows
+        self.buf: Dict[str, torch.Tensor] = {}
+        self.rows, self.cnt, self.tiles, self.max_tiles = [], [], [], []
+        for s in range(S):
+            cap = T[s] * K[s]
+            self.rows.append(torch.empty((B, cap, 4), dtype=f32, device=dev))
+            self.cnt.append(torch.empty((B, T[s]), dtype=torch.int32, device=dev))
+            mt = B * ((cap + tr - 1) // tr)
+            self.max_tiles.append(mt)
+            self.tiles.append(torch.empty((max(mt, 1), 4), dtype=torch.int32, device=dev))
+            self.buf["feat%d" % (s + 1)] = torch.empty((B, T[s], eng.ld_feat[s]), dtype=f32, device=dev)
+        self.ntiles = torch.zeros(_lib.MAX_SCALES, dtype=torch.int32, device=dev)
+        widths = (128, 256, 512, 512)[: S - 1]
+        self.buf["x1"] = torch.empty((B, T[0], arch.block1_out), dtype=f32, device=dev)
+        for i in range(2, S + 1):
+            for nm in ("a", "b", "m"):
+                self.buf["%s%d" % (nm, i)] = torch.empty((B, T[i - 1], widths[i - 2]), dtype=f32, device=dev)
+        self.buf["cat"] = torch.empty((B, T[1], 256 * (S - 1)), dtype=f32, device=dev)
+        self.buf["logits"] = torch.empty((B, T[1], eng.ld_logit), dtype=f32, device=dev)
+        T2 = T[1]
+        # the six outputs of det_base.py:411 are views into one flat block (single all-gather / D2H)
+        widths_out = (2, 3, 1, 3, eng.num_bins, eng.num_size)
+        self.out_flat = torch.empty(B * T2 * sum(widths_out), dtype=f32, device=dev)
+        outs, off = [], 0
+        for wd in widths_out:
+            n = B * T2 * wd
+            v = self.out_flat[off: off + n]
+            outs.append(v.view(B, T2) if wd == 1 and len(outs) == 2 else v.view(B, T2, wd))
+            off += n
+        self.out = tuple(outs)
+        # static inputs (graph replay reads these)
+        self.in_pc = torch.empty((B, 3, max(N, 1)), dtype=f32, device=dev)
+        self.in_centers = [torch.empty((B, 3, T[s]), dtype=f32, device=dev) for s in range(S)]
+        self.in_onehot = torch.zeros((B, max(eng.num_vec, 1)), dtype=f32, device=dev)
+        self.graph = None
+        self._build_args()
+
+    def _tsize(self, name):
+        return self.buf[name].shape[1]
+
+    def _build_args(self):
+        eng, S = self.eng, self.eng.arch.num_scales
+        g = _lib.GroupArgs()
+        g.num_scales, g.B, g.N, g.num_vec = S, self.B, self.N, eng.num_vec
+        g.tile_rows, g.unique_rows = eng.tile_rows, 1
+        for s in range(S):
+            g.T[s], g.K[s], g.dis_z[s] = self.T[s], eng.arch.nsample[s], eng.dists[s]
+            g.c3[s], g.ld_feat[s] = eng.c3[s], eng.ld_feat[s]
+            g.row_cap[s] = self.T[s] * eng.arch.nsample[s]
+            g.tile_cap[s] = max(self.max_tiles[s], 1)
+            g.rows[s], g.cnt[s] = _ptr(self.rows[s]), _ptr(self.cnt[s])
+            g.feat[s], g.tiles[s] = _ptr(self.buf["feat%d" % (s + 1)]), _ptr(self.tiles[s])
+        g.ntiles = _ptr(self.ntiles)
+        self.group_args = g
+        self.pn_args = []
+        for s in range(S if eng.has_feat else 0):
+            c1, c2, c3 = eng.arch.mlps[s]
+            a = _lib.PointnetArgs()
+            a.C1, a.C2, a.C3, a.T, a.K = c1, c2, c3, self.T[s], eng.arch.nsample[s]
+            a.ld_feat, a.row_cap, a.tile_rows = eng.ld_feat[s], self.T[s] * eng.arch.nsample[s], eng.tile_rows
+            a.unpooled, a.precision, a.B = 0, eng.precision, self.B
+            a.rows, a.tiles = _ptr(self.rows[s]), _ptr(self.tiles[s])
+            a.ntiles = self.ntiles.data_ptr() + 4 * s
+            a.max_tiles = self.max_tiles[s]
+            w = eng.pn[s]
+            a.w1t, a.b1, a.w2t, a.b2, a.w3t, a.b3 = (_ptr(w["w1t"]), _ptr(w["b1"]), _ptr(w["w2t"]),
+                                                    _ptr(w["b2"]), _ptr(w["w3t"]), _ptr(w["b3"]))
+            a.w2_tc, a.w3_tc = _ptr(w.get("w2_tc")), _ptr(w.get("w3_tc"))
+            a.out = _ptr(self.buf["feat%d" % (s + 1)])
+            self.pn_args.append(a)
+        self.conv_args = []
+        for L in eng.layers:
+            a = _lib.ConvArgs()
+            out = self.buf[L.out]
+            first_src = self.buf[L.segs[0][0]]
+            stride = L.segs[0][3]
+            a.B = self.B
+            a.T_out = first_src.shape[1] if stride == 1 else (first_src.shape[1] + 1) // 2
+            a.n_seg = len(L.segs)
+            for j, (src, c, tap, st) in enumerate(L.segs):
+                t = self.buf[src]
+                a.seg[j].src, a.seg[j].ld, a.seg[j].C = _ptr(t), t.shape[2], c
+                a.seg[j].T_src, a.seg[j].tap, a.seg[j].stride = t.shape[1], tap, st
+            a.K_pad, a.n_cols, a.Cout, a.up, a.relu = L.K_pad, L.n_cols, L.Cout, L.up, L.relu
+            a.precision = 0
+            a.wt, a.bias, a.w_tc = _ptr(L.wt), _ptr(L.bias), None
+            a.out, a.ld_out, a.T_store, a.c_off = _ptr(out), out.shape[2], out.shape[1], L.c_off
+            self.conv_args.append(a)
+
+    # ---- launch sequences (all asynchronous on the current stream)
+    def _launch_feat(self, pc, centers, one_hot):
+        g = self.group_args
+        g.pc = _ptr(pc)
+        g.one_hot = _ptr(one_hot) if self.eng.num_vec > 0 else None
+        for s, c in enumerate(centers):
+            g.centers[s] = _ptr(c)
+        st = _stream()
+        self.ntiles.zero_()
+        _lib.call("fcn_group_rows", C.byref(g), st)
+        for a in self.pn_args:
+            _lib.call("fcn_pointnet_tiles", C.byref(a), st)
+
+    def _launch_fcn(self):
+        st = _stream()
+        for a in self.conv_args:
+            _lib.call("fcn_conv_gemm", C.byref(a), st)
+
+    def _launch_decode(self, center_ref2):
+        eng = self.eng
+        o = self.out
+        _lib.call("fcn_decode_eval", self.B, self.T[1], eng.ld_logit, eng.num_bins, eng.num_size,
+                  _ptr(self.buf["logits"]), _ptr(center_ref2), _ptr(eng.mean_size), _ptr(o[0]), _ptr(o[1]),
+                  _ptr(o[2]), _ptr(o[3]), _ptr(o[4]), _ptr(o[5]), _stream())
+
+    def _check_inputs(self, pc, centers, one_hot):
+        assert pc.is_cuda and pc.dtype == torch.float32 and pc.is_contiguous()
+        assert tuple(pc.shape) == (self.B, 3, self.N)
+        for s, c in enumerate(centers):
+            assert c.is_cuda and c.dtype == torch.float32 and c.is_contiguous()
+            assert tuple(c.shape) == (self.B, 3, self.T[s])
+        if self.eng.num_vec > 0:
+            assert one_hot is not None and tuple(one_hot.shape) == (self.B, self.eng.num_vec)
+            assert one_hot.dtype == torch.float32 and one_hot.is_contiguous()
+
+    def run(self, pc, centers, one_hot, use_graph=False):
+        self._check_inputs(pc, centers, one_hot)
+        with torch.cuda.device(self.eng.device):
+            if not use_graph:
+                self._launch_feat(pc, centers, one_hot)
+                self._launch_fcn()
+                self._launch_decode(centers[1])
+                return self.out
+            self.in_pc.copy_(pc, non_blocking=True)
+            for d, c in zip(self.in_centers, centers):
+                d.copy_(c, non_blocking=True)
+            if self.eng.num_vec > 0:
+                self.in_onehot.copy_(one_hot, non_blocking=True)
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+            return self.out
+
+    def _capture(self):
+        # warm-up run outside capture (sets function attributes, loads modules)
+        self._launch_feat(self.in_pc, self.in_centers, self.in_onehot)
+        self._launch_fcn()
+        self._launch_decode(self.in_centers[1])
+        torch.cuda.current_stream().synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch_feat(self.in_pc, self.in_centers, self.in_onehot)
+            self._launch_fcn()
+            self._launch_decode(self.in_centers[1])
+        self.graph = g
+
+    def run_feat(self, pc, centers, one_hot):
+        self._check_inputs(pc, centers, one_hot)
+        eng = self.eng
+        with torch.cuda.device(eng.device):
+            self._launch_feat(pc, centers, one_hot)
+            outs = []
+            for s in range(eng.arch.num_scales):
+                c = eng.c3[s] + eng.num_vec
+                o = torch.empty((self.B, c, self.T[s]), dtype=torch.float32, device=eng.device)
+                _lib.call("fcn_btc_to_bct", self.B, c, self.T[s], eng.ld_feat[s],
+                          _ptr(self.buf["feat%d" % (s + 1)]), _ptr(o), _stream())
+                outs.append(o)
+        return tuple(outs)
+
+    def run_fcn_bct(self, feats_bct):
+        eng = self.eng
+        with torch.cuda.device(eng.device):
+            for s, f in enumerate(feats_bct):
+                c = eng.c3[s] + eng.num_vec
+                assert f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()
+                assert tuple(f.shape) == (self.B, c, self.T[s]), "feat%d has shape %s" % (s + 1, tuple(f.shape))
+                _lib.call("fcn_bct_to_btc", self.B, c, self.T[s], eng.ld_feat[s], _ptr(f),
+                          _ptr(self.buf["feat%d" % (s + 1)]), _stream())
+            st = _stream()
+            for a, L in zip(self.conv_args, eng.layers):
+                if L.name == "heads":
+                    continue
+                _lib.call("fcn_conv_gemm", C.byref(a), st)
+            cat = self.buf["cat"]
+            o = torch.empty((self.B, cat.shape[2], cat.shape[1]), dtype=torch.float32, device=eng.device)
+            _lib.call("fcn_btc_to_bct", self.B, cat.shape[2], cat.shape[1], cat.shape[2], _ptr(cat), _ptr(o), st)
+        return o
+
+    def time_kernels(self, dev_pool, iters=20):
+        """Per-kernel device time of the eager launch sequence, CUDA events on the launching stream,
+        averaged over `iters` forwards; plus executed/nominal FLOPs per launch (bench.py roofline)."""
+        eng, S = self.eng, self.eng.arch.num_scales
+        names = ["group_rows"] + ["pointnet_s%d" % (s + 1) for s in range(S)] + \
+            [L.name for L in eng.layers] + ["decode_eval"]
+        acc = np.zeros(len(names))
+        st = _stream()
+        with torch.cuda.device(eng.device):
+            for it in range(iters + 2):
+                d = dev_pool[it % len(dev_pool)]
+                centers = [d["center_ref%d" % (i + 1)] for i in range(S)]
+                g = self.group_args
+                g.pc, g.one_hot = _ptr(d["point_cloud"]), _ptr(d["one_hot"]) if eng.num_vec > 0 else None
+                for s_, c in enumerate(centers):
+                    g.centers[s_] = _ptr(c)
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                self.ntiles.zero_()
+                k = 0
+                ev[0].record()
+                _lib.call("fcn_group_rows", C.byref(g), st); k += 1; ev[k].record()
+                for a in self.pn_args:
+                    _lib.call("fcn_pointnet_tiles", C.byref(a), st); k += 1; ev[k].record()
+                for a in self.conv_args:
+                    _lib.call("fcn_conv_gemm", C.byref(a), st); k += 1; ev[k].record()
+                self._launch_decode(centers[1]); k += 1; ev[k].record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
+        acc /= iters
+        rows_exec = [int(c.sum().item()) for c in self.cnt]
+        rows_nom = [self.B * self.T[s] * eng.arch.nsample[s] for s in range(S)]
+        kern = [dict(name="group_rows", ms=float(acc[0]), executed_gflop=0.0, nominal_gflop=0.0)]
+        for s in range(S):
+            c1, c2, c3 = eng.arch.mlps[s]
+            mac = 3 * c1 + c1 * c2 + c2 * c3
+            kern.append(dict(name="pointnet_s%d" % (s + 1), ms=float(acc[1 + s]),
+                             executed_gflop=2e-9 * mac * rows_exec[s], nominal_gflop=2e-9 * mac * rows_nom[s]))
+        for j, (L, a) in enumerate(zip(eng.layers, self.conv_args)):
+            kreal = sum(sg[1] for sg in L.segs)
+            nreal = (2 + eng.out_size) if L.name == "heads" else L.up * L.Cout
+            gf = 2e-9 * a.B * a.T_out * kreal * nreal
+            kern.append(dict(name=L.name, ms=float(acc[1 + S + j]), executed_gflop=gf, nominal_gflop=gf))
+        kern.append(dict(name="decode_eval", ms=float(acc[-1]), executed_gflop=0.0, nominal_gflop=0.0))
+        for k_ in kern:
+            k_["executed_tflops"] = k_["executed_gflop"] / max(k_["ms"], 1e-9)  # GFLOP/ms == TFLOP/s
+        return dict(kernels=kern, launches_per_step=len(names),
+                    unique_row_fraction=float(sum(rows_exec)) / float(max(sum(rows_nom), 1)))
+
+    def logits(self):
+        """(B*T2, 2) class scores and (B*T2, out) regression rows of the last run (views)."""
+        lg = self.buf["logits"].view(-1, self.eng.ld_logit)
+        return lg[:, 0:2], lg[:, 2:2 + self.eng.out_size]
+
+
+def _run_module(eng: FrustumEngine, scale: int, pc, new_pc):
+    """PointNetModule.forward (det_base.py:62-103): un-pooled masked (B,C3,T,K)."""
+    assert pc.is_cuda and pc.is_contiguous() and new_pc.is_contiguous()
+    B, N, T = pc.shape[0], pc.shape[2], new_pc.shape[2]
+    K = eng.arch.nsample[scale]
+    c1, c2, c3 = eng.arch.mlps[scale]
+    dev, f32 = eng.device, torch.float32
+    tr = 64
+    with torch.cuda.device(dev):
+        rows = torch.empty((B, T * K, 4), dtype=f32, device=dev)
+        cnt = torch.empty((B, T), dtype=torch.int32, device=dev)
+        mt = B * ((T * K + tr - 1) // tr)
+        tiles = torch.empty((max(mt, 1), 4), dtype=torch.int32, device=dev)
+        ntiles = torch.zeros(_lib.MAX_SCALES, dtype=torch.int32, device=dev)
+        out = torch.empty((B, c3, T, K), dtype=f32, device=dev)
+        g = _lib.GroupArgs()
+        g.num_scales, g.B, g.N, g.num_vec, g.tile_rows, g.unique_rows = 1, B, N, 0, tr, 0
+        g.pc, g.one_hot = _ptr(pc), None
+        g.centers[0], g.T[0], g.K[0], g.dis_z[0] = _ptr(new_pc), T, K, eng.dists[scale]
+        g.c3[0], g.ld_feat[0], g.row_cap[0], g.tile_cap[0] = c3, 0, T * K, max(mt, 1)
+        g.rows[0], g.cnt[0], g.feat[0], g.tiles[0] = _ptr(rows), _ptr(cnt), None, _ptr(tiles)
+        g.ntiles = _ptr(ntiles)
+        st = _stream()
+        _lib.call("fcn_group_rows", C.byref(g), st)
+        a = _lib.PointnetArgs()
+        a.C1, a.C2, a.C3, a.T, a.K = c1, c2, c3, T, K
+        a.ld_feat, a.row_cap, a.tile_rows, a.unpooled, a.precision, a.B = 0, T * K, tr, 1, 0, B
+        a.rows, a.tiles, a.ntiles, a.max_tiles = _ptr(rows), _ptr(tiles), _ptr(ntiles), mt
+        w = eng.pn[scale]
+        a.w1t, a.b1, a.w2t, a.b2, a.w3t, a.b3 = (_ptr(w["w1t"]), _ptr(w["b1"]), _ptr(w["w2t"]),
+                                                _ptr(w["b2"]), _ptr(w["w3t"]), _ptr(w["b3"]))
+        a.out = _ptr(out)
+        _lib.call("fcn_pointnet_tiles", C.byref(a), st)
+    return out

@@ -1,0 +1,160 @@
+/*
+ * frustum_b200.h — C ABI of libfrustum_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the per-frustum hot path of Gorilla-Lab-SCUT/frustum-convnet:
+ *   ops/query_depth_point  ->  models/det_base.PointNetFeat  ->  ConvFeatNet  ->  heads/decode.
+ *
+ * Conventions:
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name says host;
+ *   - the caller owns every buffer (the reference allocates outputs in Python and passes them
+ *     in: ops/query_depth_point/query_depth_point.py:36-39); the library allocates nothing and
+ *     keeps no state between calls except a thread-local error string;
+ *   - `stream` is a cudaStream_t passed as void* (the reference launches on ATen's current
+ *     stream: query_depth_point_cuda_kernel.cu:72); all calls are asynchronous;
+ *   - return 0 on success, <0 on error (no C++ exception crosses the ABI; the reference raised
+ *     through AT_ASSERTM / THCudaCheck: query_depth_point_cuda.cpp:5-10, ..._kernel.cu:85);
+ *     fcn_last_error() returns the message of the last failing call on this thread.
+ */
+#ifndef FRUSTUM_B200_H_
+#define FRUSTUM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCN_OK 0
+#define FCN_ERR_INVALID (-1)
+#define FCN_ERR_CUDA (-2)
+
+#define FCN_MAX_SCALES 8
+#define FCN_MAX_SEGS 4
+
+#if defined(__GNUC__)
+#define FCN_API __attribute__((visibility("default")))
+#else
+#define FCN_API
+#endif
+
+typedef void *fcn_stream_t;
+
+FCN_API int fcn_version(void);
+FCN_API const char *fcn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Grouping op.  Replaces query_depth_point_cuda.forward(b,n,m,dis_z,nsample,xyz1,xyz2,idx,
+ *     pts_cnt) bound at ops/query_depth_point/query_depth_point_cuda.cpp:25-50 (kernel
+ *     query_depth_point_cuda_kernel.cu:16-86).  Same argument order and meaning.
+ *     idx: (b,m,nsample) int64, pts_cnt: (b,m) int32; both fully written (no pre-zero needed).
+ *     _bn3  : xyz1 (b,n,3), xyz2 (b,m,3)   — the layout the reference kernel receives.
+ *     _b3n  : xyz1 (b,3,n), xyz2 (b,3,m)   — the layout QueryDepthPoint.forward receives
+ *             (query_depth_point.py:18-19); saves the two permute().contiguous() copies (:29-30).
+ * ------------------------------------------------------------------------------------------ */
+FCN_API int fcn_query_depth_point_bn3(int b, int n, int m, float dis_z, int nsample, const float *xyz1,
+                              const float *xyz2, int64_t *idx, int32_t *pts_cnt,
+                              fcn_stream_t stream);
+FCN_API int fcn_query_depth_point_b3n(int b, int n, int m, float dis_z, int nsample, const float *xyz1,
+                              const float *xyz2, int64_t *idx, int32_t *pts_cnt,
+                              fcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Fused grouping -> row records (feeds the PointNet tile kernels; replaces
+ *     QueryDepthPoint + torch.gather + "grouped_pc - new_pc", models/det_base.py:68-80,
+ *     for all scales of PointNetFeat in ONE launch).
+ *
+ *     For every (frustum b, scale s) the T_s sections are scanned; section t contributes
+ *     cnt = min(hits, K_s) rows (unique_rows=1) or exactly K_s rows with the reference's
+ *     back-fill duplicates (unique_rows=0).  A row record is float4 {x-cx, y-cy, z-cz, bits(t)}
+ *     (bits(t) = section index as int; sign bit set when the section is empty/masked).
+ *     Rows of (b,s) are stored contiguously at rows[s] + b*row_cap[s]; tiles of `tile_rows`
+ *     rows are appended to tiles[s] (int4 {b, row0, nrows, 0}) and counted in ntiles[s].
+ *     Side outputs: cnt[s] (B,T_s) int32; feat[s] (B,T_s,ld_feat[s]) fp32 position-major is
+ *     zero-filled and its one-hot channels [c3[s], c3[s]+num_vec) are written (det_base.py:145-157).
+ *     `ntiles` (int32[FCN_MAX_SCALES]) must be zero before the call (cudaMemsetAsync by caller).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int num_scales, B, N, num_vec, tile_rows, unique_rows;
+    const float *pc;                        /* (B,3,N) */
+    const float *one_hot;                   /* (B,num_vec) or NULL */
+    const float *centers[FCN_MAX_SCALES];   /* (B,3,T_s) */
+    int T[FCN_MAX_SCALES], K[FCN_MAX_SCALES];
+    float dis_z[FCN_MAX_SCALES];
+    int c3[FCN_MAX_SCALES], ld_feat[FCN_MAX_SCALES];
+    int row_cap[FCN_MAX_SCALES];            /* rows reserved per frustum (>= T_s*K_s) */
+    int tile_cap[FCN_MAX_SCALES];           /* capacity of tiles[s] */
+    void *rows[FCN_MAX_SCALES];             /* float4[B*row_cap] */
+    int32_t *cnt[FCN_MAX_SCALES];           /* (B,T_s) */
+    float *feat[FCN_MAX_SCALES];            /* (B,T_s,ld_feat) or NULL */
+    void *tiles[FCN_MAX_SCALES];            /* int4[tile_cap] */
+    int32_t *ntiles;                        /* int32[FCN_MAX_SCALES] */
+} fcn_group_args;
+FCN_API int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) PointNet tile kernel: three folded (conv1x1 + BN + ReLU) layers on row tiles and the
+ *     max over the rows of each section.  Replaces models/det_base.py:95-101 + torch.max(-1)
+ *     (:134-143) for one scale.
+ *     Weights are BN-folded and packed by the host side:
+ *       w1t (3,C1)  w2t (C1,C2)  w3t (C2,C3)  fp32 row-major [cin][cout];  b1,b2,b3 fp32.
+ *     pooled   : out = feat (B,T,ld_feat) position-major, combined with atomic max (feat must be
+ *                zero-initialised, which fcn_group_rows does).
+ *     unpooled : out = (B,C3,T,K) channel-first un-pooled masked tensor — the return value of
+ *                PointNetModule.forward (det_base.py:103); rows must come from unique_rows=0.
+ *     precision: 0 = fp32 SIMT, 1 = TF32 tensor cores (tcgen05) for the C1->C2->C3 layers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int C1, C2, C3, T, K, ld_feat, row_cap, tile_rows, unpooled, precision, B;
+    const void *rows;       /* float4 records of this scale */
+    const void *tiles;      /* int4 tile table */
+    const int32_t *ntiles;  /* device scalar */
+    int max_tiles;          /* host upper bound used to size the grid */
+    const float *w1t, *b1, *w2t, *b2, *w3t, *b3;
+    const void *w2_tc, *w3_tc;  /* tensor-core packed images (precision=1), else NULL */
+    float *out;
+} fcn_pointnet_args;
+FCN_API int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) 1-D conv / transposed conv / 1x1 conv + folded BN + optional ReLU as an implicit GEMM on
+ *     position-major activations.  Replaces every Conv1d/DeConv1d block of ConvFeatNet
+ *     (models/det_base.py:167-224, factories models/common.py:38-63), the torch.cat calls
+ *     (multi-segment A operand) and the two heads (det_base.py:367-368).
+ *       out[b, t*up + j, c_off + co] = act( sum_seg sum_c src[b, t*stride + tap, c] * W + bias )
+ *     K is the concatenation of the segments, each padded to a multiple of 32 (zero weights).
+ *     wt: [K_pad][n_cols] fp32 (n_cols = up*Cout rounded up to 64), bias: [n_cols].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float *src;
+    int ld, C, T_src, tap, stride;
+} fcn_conv_seg;
+typedef struct {
+    int B, T_out, n_seg;
+    fcn_conv_seg seg[FCN_MAX_SEGS];
+    int K_pad, n_cols, Cout, up, relu, precision;
+    const float *wt, *bias;
+    const void *w_tc;
+    float *out;
+    int ld_out, T_store, c_off;
+} fcn_conv_args;
+FCN_API int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) Eval decode of the head logits.  Replaces models/det_base.py:376-411 and
+ *     models/box_transform.py:5-12,28-41.
+ *     logits: (B*T, ld) rows = [cls0, cls1, center(3), heading scores(NH), heading res(NH),
+ *     size scores(NS), size res(NS*3)];  center_ref: (B,3,T) channel-first;  mean_size (NS,3).
+ * ------------------------------------------------------------------------------------------ */
+FCN_API int fcn_decode_eval(int B, int T, int ld, int num_heading_bin, int num_size, const float *logits,
+                    const float *center_ref, const float *mean_size, float *cls_probs,
+                    float *center, float *heading, float *size, float *heading_probs,
+                    float *size_probs, fcn_stream_t stream);
+
+/* Layout helpers for the channel-first module APIs: (B,C,T) <-> (B,T,ld). */
+FCN_API int fcn_bct_to_btc(int B, int C, int T, int ld, const float *src, float *dst, fcn_stream_t stream);
+FCN_API int fcn_btc_to_bct(int B, int C, int T, int ld, const float *src, float *dst, fcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRUSTUM_B200_H_ */

@@ -1,0 +1,80 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol declared in include/*.h
+(no compute call is made without a GPU), and the host-side mirror behaves like the reference."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "frustum_b200.h")).read()
+    return sorted(set(re.findall(r"FCN_API\s+[\w\s\*]*?\b(fcn_\w+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_every_header_symbol():
+    from frustum_convnet_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+        assert s in _lib.SIGNATURES, "ctypes signature table lacks " + s
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert lib.fcn_version() >= 100
+
+
+def test_argument_validation_without_gpu():
+    """Validation happens before any CUDA call, so error codes are testable on CPU."""
+    from frustum_convnet_b200 import _lib
+    lib = _lib.load()
+    assert lib.fcn_query_depth_point_b3n(1, 4, 4, 0.5, 0, None, None, None, None, None) == -1
+    assert b"nsample" in lib.fcn_last_error()
+    assert lib.fcn_query_depth_point_b3n(0, 4, 4, 0.5, 4, None, None, None, None, None) == 0  # empty batch
+    assert lib.fcn_group_rows(None, None) == -1
+    assert lib.fcn_decode_eval(1, 1, 8, 12, 3, None, None, None, None, None, None, None, None, None, None) == -1
+    with pytest.raises(RuntimeError):
+        _lib.call("fcn_conv_gemm", None, None)
+
+
+def test_cpu_tensors_are_rejected_like_the_reference():
+    """query_depth_point.py:23-24 asserts .is_cuda; there is no CPU path here either."""
+    from frustum_convnet_b200.query_depth_point import QueryDepthPoint
+    q = QueryDepthPoint(0.25, 8)
+    with pytest.raises(AssertionError):
+        q(torch.zeros(1, 3, 16), torch.zeros(1, 3, 4))
+
+
+def test_state_dict_names_match_reference_layout(golden_loader):
+    from frustum_convnet_b200 import config
+    for name, modname in (("car_small_b3", "det_base"), ("sunrgbd_full_b2", "det_base_sunrgbd")):
+        g, data, sd, w, cfg = golden_loader(name)
+        mod = __import__("frustum_convnet_b200." + modname, fromlist=["PointNetDet"])
+        m = mod.PointNetDet(3, num_vec=w["num_vec"])
+        res = m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        n = sum(p.numel() for p in m.parameters())
+        assert n == (3316777 if modname == "det_base" else 6667589)
+        with pytest.raises(RuntimeError):   # eval forward on CPU must fail loudly, not fall back
+            m.eval()
+            m({k: torch.from_numpy(v) for k, v in data.items()})
+
+
+def test_engine_weight_pack_is_a_pure_function_of_the_state_dict(golden_loader):
+    """BN folding on the host (CPU tensors here): folded 1x1 weights reproduce conv+BN."""
+    from frustum_convnet_b200.engine import _fold_bn
+    g, data, sd, w, cfg = golden_loader("car_small_b3")
+    tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    p = "feat_net.pointnet1.conv1"
+    s, sh = _fold_bn(tsd, p + ".1")
+    x = torch.randn(5, 3, dtype=torch.float64)
+    wq = tsd[p + ".0.weight"].double()[:, :, 0, 0]
+    ref = torch.nn.functional.batch_norm(
+        (x @ wq.t()).float(), tsd[p + ".1.running_mean"], tsd[p + ".1.running_var"],
+        tsd[p + ".1.weight"], tsd[p + ".1.bias"], False, 0.1, 1e-5)
+    mine = x @ (wq * s[:, None]).t() + sh
+    assert torch.allclose(ref.double(), mine, atol=1e-5)

@@ -1,0 +1,243 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI) against the oracle and the golden
+fixtures produced by the reference itself.
+
+Tolerances: grouping indices / counts are BIT-EXACT.  Floating-point tensors of the fp32 path
+must agree within  max|a-b| <= 2e-4 * max(1, max|ref|)  (fp32 accumulation-order differences
+only: BN is folded into the weights and sums run in a different order than oneDNN's).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 2e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def close(a, b, tol=FP32_TOL, what=""):
+    a = a.detach().float().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, "%s shape %s vs %s" % (what, a.shape, b.shape)
+    err = float(np.abs(a - b).max()) if a.size else 0.0
+    lim = tol * max(1.0, float(np.abs(b).max()) if b.size else 1.0)
+    assert err <= lim, "%s: max abs err %.3e > %.3e" % (what, err, lim)
+
+
+def cuda_data(data):
+    return {k: torch.from_numpy(v).to(dev()) for k, v in data.items()}
+
+
+def build_model(w, sd, workload_cfg):
+    modname = "det_base_sunrgbd" if w["arch"].num_scales == 5 else "det_base"
+    mod = __import__("frustum_convnet_b200." + modname, fromlist=["PointNetDet"])
+    m = mod.PointNetDet(3, num_vec=w["num_vec"])
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return m.to(dev()).eval()
+
+
+# ------------------------------------------------------------------ grouping (bit-exact)
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_query_depth_point_matches_golden_bit_exact(name):
+    from frustum_convnet_b200.query_depth_point import QueryDepthPoint, query_depth_point_bn3
+    g, data, sd, w, cfg = load_golden(name)
+    d = cuda_data(data)
+    for i in range(w["arch"].num_scales):
+        q = QueryDepthPoint(cfg.DATA.HEIGHT_HALF[i], w["arch"].nsample[i])
+        idx, cnt = q(d["point_cloud"], d["center_ref%d" % (i + 1)])
+        assert idx.dtype == torch.int64 and cnt.dtype == torch.int32
+        assert np.array_equal(idx.cpu().numpy(), g["idx%d" % (i + 1)].astype(np.int64))
+        assert np.array_equal(cnt.cpu().numpy(), g["cnt%d" % (i + 1)].astype(np.int32))
+        # the reference's native calling convention: (b,n,3) inputs, caller-owned outputs
+        x1 = d["point_cloud"].permute(0, 2, 1).contiguous()
+        x2 = d["center_ref%d" % (i + 1)].permute(0, 2, 1).contiguous()
+        idx2 = torch.full_like(idx, -7)
+        cnt2 = torch.full_like(cnt, -7)
+        query_depth_point_bn3(q.dis_z, q.nsample, x1, x2, idx2, cnt2)
+        assert torch.equal(idx2, idx) and torch.equal(cnt2, cnt)
+
+
+def test_query_depth_point_random_and_edge_cases():
+    from oracle import qdp
+    from frustum_convnet_b200.query_depth_point import query_depth_point
+    rng = np.random.default_rng(3)
+    cases = [(2, 50, 10, 4, 0.2), (3, 1000, 77, 32, 0.1), (1, 33, 5, 64, 0.5), (2, 31, 9, 3, 0.3),
+             (4, 2048, 80, 256, 0.8), (1, 1, 1, 1, 1.0), (2, 64, 8, 8, 1e-9)]
+    for (B, N, M, K, dz) in cases:
+        a = (rng.random((B, 3, N)) * 4 - 2).astype(np.float32)
+        b = (rng.random((B, 3, M)) * 4 - 2).astype(np.float32)
+        a[:, 2, ::7] = a[:, 2, 0:1]            # duplicates
+        if N > 5:
+            a[0, 2, 3] = np.nan                # NaN depth is never selected
+            b[0, 2, 0] = a[0, 2, 1] + np.float32(dz)   # |dz| == dis_z boundary (strict <)
+        ri, rc = qdp.qdp_c(a, b, dz, K)
+        gi, gc = query_depth_point(dz, K, torch.from_numpy(a).to(dev()), torch.from_numpy(b).to(dev()))
+        assert np.array_equal(gi.cpu().numpy(), ri), (B, N, M, K, dz)
+        assert np.array_equal(gc.cpu().numpy(), rc)
+
+
+def test_query_depth_point_full_size_car_b32():
+    """BASELINE.json configs[1] size: B=32 x 1024 points, all four scales, bit-exact."""
+    from oracle import qdp
+    from frustum_convnet_b200 import config, synth
+    from frustum_convnet_b200.query_depth_point import query_depth_point
+    cfg, w = config.load_workload("car")
+    data = synth.make_frustums("car", 32, seed=2024)
+    pc = torch.from_numpy(data["point_cloud"]).to(dev())
+    for i in range(4):
+        c = data["center_ref%d" % (i + 1)]
+        ri, rc = qdp.qdp_c(data["point_cloud"], c, cfg.DATA.HEIGHT_HALF[i], w["arch"].nsample[i])
+        gi, gc = query_depth_point(cfg.DATA.HEIGHT_HALF[i], w["arch"].nsample[i], pc,
+                                   torch.from_numpy(c).to(dev()))
+        assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(gc.cpu().numpy(), rc)
+        # size-independent properties: ascending unique prefix, back-fill equals first hit
+        gi_np, gc_np = gi.cpu().numpy(), gc.cpu().numpy()
+        k = np.arange(gi_np.shape[2])[None, None, :]
+        valid = k < gc_np[:, :, None]
+        inc = np.diff(gi_np, axis=2) > 0
+        assert np.all(inc | ~valid[:, :, 1:])
+        assert np.all(np.where(valid, True, gi_np == gi_np[:, :, :1]))
+
+
+# ------------------------------------------------------------------ PointNet feature extractor
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_pointnet_feat_matches_golden(name):
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    d = cuda_data(data)
+    S = w["arch"].num_scales
+    feats = m.feat_net(d["point_cloud"], [d["center_ref%d" % (i + 1)] for i in range(S)], None, d["one_hot"])
+    assert len(feats) == S
+    for i, f in enumerate(feats):
+        close(f, g["feat%d" % (i + 1)], what="%s feat%d" % (name, i + 1))
+
+
+@pytest.mark.parametrize("name", ["car_small_b3", "sunrgbd_full_b2"])
+def test_pointnet_module_unpooled_matches_oracle(name):
+    """API #2: PointNetModule.forward returns the masked, un-pooled (B,C3,T,K) tensor."""
+    from oracle import model as om
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    d = cuda_data(data)
+    tsd = om.to_torch_state(sd)
+    pc = torch.from_numpy(data["point_cloud"])
+    for i in (0, w["arch"].num_scales - 1):
+        mod = getattr(m.feat_net, "pointnet%d" % (i + 1))
+        out = mod(d["point_cloud"], None, d["center_ref%d" % (i + 1)])
+        ref, _, _ = om.pointnet_module(pc, torch.from_numpy(data["center_ref%d" % (i + 1)]), tsd,
+                                       "feat_net.pointnet%d" % (i + 1), cfg.DATA.HEIGHT_HALF[i],
+                                       w["arch"].nsample[i])
+        close(out, ref, what="%s module%d" % (name, i + 1))
+
+
+# ------------------------------------------------------------------ FCN + heads + decode
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_conv_feat_net_matches_golden(name):
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    S = w["arch"].num_scales
+    feats = [torch.from_numpy(g["feat%d" % (i + 1)]).to(dev()) for i in range(S)]
+    x = m.conv_net(*feats)
+    close(x, g["x"], what=name + " conv_net")
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_pointnet_det_forward_matches_golden(name):
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    d = cuda_data(data)
+    out = m(d)
+    assert isinstance(out, tuple) and len(out) == 6
+    B = data["point_cloud"].shape[0]
+    plan = m.engine().plan(B, data["point_cloud"].shape[2],
+                           [data["center_ref%d" % (i + 1)].shape[2] for i in range(w["arch"].num_scales)])
+    cls, reg = plan.logits()
+    close(cls.view(B, -1, 2).permute(0, 2, 1), g["cls"], what=name + " cls logits")
+    close(reg.view(B, -1, reg.shape[1]).permute(0, 2, 1), g["reg"], what=name + " reg logits")
+    # decoded tuple: positions whose argmax is numerically ambiguous are excluded for the
+    # label-dependent outputs (heading, size); probabilities and centres are compared everywhere
+    close(out[0], g["out0"], what="cls_probs")
+    close(out[1], g["out1"], what="center")
+    close(out[4], g["out4"], tol=1e-3, what="heading_probs")
+    close(out[5], g["out5"], tol=1e-3, what="size_probs")
+    hp, sp = np.sort(g["out4"], -1), np.sort(g["out5"], -1)
+    ok = ((hp[..., -1] - hp[..., -2]) > 1e-3) & ((sp[..., -1] - sp[..., -2]) > 1e-3)
+    assert ok.mean() > 0.9
+    close(out[2].cpu().numpy()[ok], g["out2"][ok], tol=1e-3, what="heading")
+    close(out[3].cpu().numpy()[ok], g["out3"][ok], tol=1e-3, what="size")
+
+
+@pytest.mark.parametrize("name", ["car_small_b3", "sunrgbd_full_b2"])
+def test_decode_kernel_on_reference_logits(name):
+    """Feed the reference's own logits to the decode kernel: isolates box decode from GEMM error."""
+    import ctypes as C
+    from frustum_convnet_b200 import _lib
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    eng = m.engine()
+    B, T = g["cls"].shape[0], g["cls"].shape[2]
+    lg = torch.zeros((B, T, eng.ld_logit), dtype=torch.float32)
+    lg[:, :, 0:2] = torch.from_numpy(g["cls"]).permute(0, 2, 1)
+    lg[:, :, 2:2 + eng.out_size] = torch.from_numpy(g["reg"]).permute(0, 2, 1)
+    lg = lg.to(dev()).contiguous()
+    ref2 = torch.from_numpy(data["center_ref2"]).to(dev())
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev())
+    o = (f(B, T, 2), f(B, T, 3), f(B, T), f(B, T, 3), f(B, T, eng.num_bins), f(B, T, eng.num_size))
+    _lib.call("fcn_decode_eval", B, T, eng.ld_logit, eng.num_bins, eng.num_size, lg.data_ptr(),
+              ref2.data_ptr(), eng.mean_size.data_ptr(), *[t.data_ptr() for t in o],
+              torch.cuda.current_stream().cuda_stream)
+    for j in range(6):
+        close(o[j], g["out%d" % j], tol=2e-6, what="decode out%d" % j)
+
+
+# ------------------------------------------------------------------ whole-path properties at full size
+def test_full_size_car_b32_properties_and_oracle():
+    """BASELINE.json configs[1]: B=32 car.  (i) equals the oracle within tolerance, (ii) frustums
+    are independent: reversing the batch reverses the outputs bit-exactly, (iii) idempotent,
+    (iv) CUDA-graph replay == eager."""
+    from oracle import model as om
+    from frustum_convnet_b200 import config, synth
+    cfg, w = config.load_workload("car")
+    sd = synth.make_state_dict(w["arch"], 3, "KITTI", seed=21)
+    m = build_model(w, sd, cfg)
+    data = synth.make_frustums("car", 32, seed=77)
+    d = cuda_data(data)
+    out = [o.clone() for o in m(d)]
+    ref = om.pointnet_det_eval(data, om.to_torch_state(sd), cfg.DATA.HEIGHT_HALF, w["arch"].nsample,
+                               config.DATASET_INFO["KITTI"].MEAN_SIZE_ARRAY)
+    for j in (0, 1, 4, 5):
+        close(out[j], ref[j], tol=1e-3, what="full-size out%d" % j)
+    out2 = [o.clone() for o in m(d)]
+    for a, b in zip(out, out2):
+        assert torch.equal(a, b)
+    drev = {k: v.flip(0).contiguous() for k, v in d.items()}
+    out3 = m(drev)
+    for a, b in zip(out, out3):
+        assert torch.equal(a, b.flip(0))
+    m.use_cuda_graph = True
+    out4 = [o.clone() for o in m(d)]
+    out5 = m(d)
+    for a, b, c in zip(out, out4, out5):
+        assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_empty_and_degenerate_inputs():
+    """All-empty sections (points far from every centre) give zero features; B=1, tiny T."""
+    from frustum_convnet_b200 import config, synth
+    cfg, w = config.load_workload("car")
+    sd = synth.make_state_dict(w["arch"], 3, "KITTI", seed=5)
+    m = build_model(w, sd, cfg)
+    data = synth.make_frustums("car", 1, seed=9, max_depth=4.0)   # T = (16, 8, 4, 2)
+    data["point_cloud"][:, 2, :] += 1000.0                        # nothing within reach
+    d = cuda_data(data)
+    feats = m.feat_net(d["point_cloud"], [d["center_ref%d" % (i + 1)] for i in range(4)], None, d["one_hot"])
+    for f in feats:
+        assert float(f[:, :-3, :].abs().max()) == 0.0
+        assert torch.equal(f[:, -3:, :], d["one_hot"].unsqueeze(-1).expand(-1, -1, f.shape[-1]))
+    out = m(d)
+    assert all(torch.isfinite(o).all() for o in out)
