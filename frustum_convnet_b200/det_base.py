@@ -194,7 +194,8 @@ class PointNetDet(_EngineOwner):
         nn.init.kaiming_uniform_(self.reg_out.weight, mode="fan_in")
         self.cls_out.bias.data.zero_()
         self.reg_out.bias.data.zero_()
-        self.use_cuda_graph = False
+        self.use_cuda_graph = False   # replay one CUDA graph per input shape
+        self.copy_outputs = True      # False: return views of the engine's output block (zero-copy)
 
     def _engine_spec(self):
         return self.ARCH, self.num_vec, self.dataset_name, self.feat_net.dists, self.num_bins, ""
@@ -212,5 +213,5 @@ class PointNetDet(_EngineOwner):
         xyz = point_cloud[:, :3, :].contiguous()
         out = self.engine().forward(xyz, [c.contiguous() for c in centers],
                                     None if one_hot_vec is None else one_hot_vec.contiguous(),
-                                    use_graph=self.use_cuda_graph)
+                                    use_graph=self.use_cuda_graph, copy_out=self.copy_outputs)
         return tuple(out)

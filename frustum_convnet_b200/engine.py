@@ -173,10 +173,11 @@ class FrustumEngine:
 
     # ------------------------------------------------------------------ public calls
     @torch.no_grad()
-    def forward(self, pc: torch.Tensor, centers: Sequence[torch.Tensor], one_hot, use_graph=False):
+    def forward(self, pc: torch.Tensor, centers: Sequence[torch.Tensor], one_hot, use_graph=False,
+                copy_out=True):
         """Eval forward -> the 6-tuple of det_base.py:411."""
         p = self.plan(pc.shape[0], pc.shape[2], [c.shape[2] for c in centers])
-        return p.run(pc, centers, one_hot, use_graph=use_graph)
+        return p.run(pc, centers, one_hot, use_graph=use_graph, copy_out=copy_out)
 
     @torch.no_grad()
     def pointnet_feat(self, pc, centers, one_hot):
@@ -342,7 +343,20 @@ class _Plan:
             assert one_hot is not None and tuple(one_hot.shape) == (self.B, self.eng.num_vec)
             assert one_hot.dtype == torch.float32 and one_hot.is_contiguous()
 
-    def run(self, pc, centers, one_hot, use_graph=False):
+    def _views(self, flat):
+        outs, off = [], 0
+        for o in self.out:
+            outs.append(flat[off: off + o.numel()].view(o.shape))
+            off += o.numel()
+        return tuple(outs)
+
+    def run(self, pc, centers, one_hot, use_graph=False, copy_out=True):
+        """copy_out=True returns fresh tensors (reference semantics); False returns views of the
+        plan's output block, which the next call overwrites (zero-copy serving / benchmarking)."""
+        out = self._run(pc, centers, one_hot, use_graph)
+        return self._views(self.out_flat.clone()) if copy_out else out
+
+    def _run(self, pc, centers, one_hot, use_graph=False):
         self._check_inputs(pc, centers, one_hot)
         with torch.cuda.device(self.eng.device):
             if not use_graph:
