@@ -77,6 +77,7 @@ SIGNATURES = {
     "fcn_decode_eval": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fcn_bct_to_btc": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _P, _P, _P]),
+    "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -4,6 +4,7 @@
 
 namespace fcn {
 int pointnet_tiles_simt(const fcn_pointnet_args &a, cudaStream_t stream);
+int pointnet_tiles_tc(const fcn_pointnet_args &a, cudaStream_t stream);
 int conv_gemm_simt(const fcn_conv_args &a, cudaStream_t stream);
 }  // namespace fcn
 
@@ -22,7 +23,8 @@ extern "C" int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t st
         FCN_REQUIRE(a.w2t && a.w3t, "NULL weight pointer");
         return pointnet_tiles_simt(a, (cudaStream_t)stream);
     }
-    return invalid(__func__, "precision must be 0 (fp32 SIMT) in this build");
+    if (a.precision == 1) return pointnet_tiles_tc(a, (cudaStream_t)stream);
+    return invalid(__func__, "precision must be 0 (fp32 SIMT) or 1 (TF32 tcgen05)");
 }
 
 extern "C" int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream) {

@@ -1,0 +1,321 @@
+// PointNet tile kernel, TF32 tensor-core variant ("precision = 1"): tcgen05.mma (kind::tf32) with
+// TMEM accumulators, weight tiles staged by the TMA engine (1-D bulk copies of pre-swizzled
+// images, mbarrier ring), warp-specialised roles.
+//
+// Per 128-row tile (rows = unique grouped points {dx,dy,dz,section} from group_rows_kernel):
+//   compute warps : layer 1 (3->C1, fp32 FMA, folded BN, ReLU) -> A operand in shared memory
+//                   (K-major, 128B swizzle, values rounded to TF32 with cvt.rna)
+//   MMA warp      : layer 2  D2[128 x C2] = A1 * W2^T          (accumulators in TMEM cols [0,C2))
+//   compute warps : TMEM -> registers, +bias, ReLU, cvt.rna -> A operand (same buffer)
+//   MMA warp      : layer 3  D3[128 x 128-col chunk] = A2 * W3^T, double-buffered TMEM chunks
+//   compute warps : TMEM -> registers, +bias, ReLU, segmented max over the rows of each section
+//                   (redux.sync per column), integer atomicMax into the position-major feature map
+//   loader warp   : streams (or keeps resident) the pre-swizzled W2/W3 stage images.
+// Replaces /root/reference/models/det_base.py:95-101 + the torch.max of :134-143 for one scale.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace fcn {
+using namespace umma;
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_COMPUTE_WARPS = 8;
+constexpr int TC_THREADS = (TC_COMPUTE_WARPS + 2) * 32;
+constexpr int TC_STAGE_BYTES = 16384;
+constexpr int TC_SLAB_COLS = 16;              // epilogue-3 transposition slab: 32 rows x 16 columns per warp
+constexpr int TC_SLAB_LD = TC_SLAB_COLS + 4;  // +4 floats: conflict-free float4 row writes / column reads
+
+template <int C1, int C2, int C3>
+struct TcCfg {
+    static constexpr int KB1 = C1 / 32, KB2 = C2 / 32;
+    static constexpr int KBMAX = KB1 > KB2 ? KB1 : KB2;
+    static constexpr int N2 = C2 < 128 ? C2 : 128;
+    static constexpr int NCH2 = C2 / N2;
+    static constexpr int N3 = 128;
+    static constexpr int NCH3 = C3 / N3;
+    static constexpr int A_BYTES = TC_ROWS * (C1 > C2 ? C1 : C2) * 4;
+    static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
+    static constexpr int NSTAGE = (C1 >= 256) ? 4 : (C1 >= 128 ? 8 : JOBS);
+    static constexpr bool RESIDENT = JOBS <= NSTAGE;
+    static constexpr int OFF_W = A_BYTES;
+    static constexpr int OFF_RECS = OFF_W + NSTAGE * TC_STAGE_BYTES;
+    static constexpr int OFF_W1 = OFF_RECS + 2 * TC_ROWS * 16;       // recs are double-buffered by tile parity
+    static constexpr int OFF_B2 = OFF_W1 + C1 * 16;
+    static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
+    static constexpr int OFF_SECT = OFF_B3 + C3 * 4;                 // int sect[128]
+    static constexpr int OFF_SLAB = OFF_SECT + 2 * TC_ROWS * 4;      // per-warp [32][TC_SLAB_LD] fp32
+    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * 32 * TC_SLAB_LD * 4;
+    static constexpr int NBAR = 2 * NSTAGE + KBMAX + 1 + 4;
+    static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+    static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
+    static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 128 == 0, "channel counts");
+    static_assert(C2 <= 256, "acc2 occupies TMEM columns [0,256)");
+};
+
+template <int C1, int C2, int C3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
+    using Cfg = TcCfg<C1, C2, C3>;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t *sA = smem;
+    uint8_t *sW = smem + Cfg::OFF_W;
+    float4 *recs_all = (float4 *)(smem + Cfg::OFF_RECS);
+    float4 *w1s = (float4 *)(smem + Cfg::OFF_W1);
+    float *b2s = (float *)(smem + Cfg::OFF_B2);
+    float *b3s = (float *)(smem + Cfg::OFF_B3);
+    int *sect_all = (int *)(smem + Cfg::OFF_SECT);
+    uint64_t *bars = (uint64_t *)(smem + Cfg::OFF_BAR);
+    uint64_t *w_full = bars, *w_empty = bars + Cfg::NSTAGE;
+    uint64_t *a_ready = bars + 2 * Cfg::NSTAGE;
+    uint64_t *acc2_full = a_ready + Cfg::KBMAX;
+    uint64_t *acc3_full = acc2_full + 1, *acc3_empty = acc3_full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = min(*p.ntiles, p.max_tiles);
+    if ((int)blockIdx.x >= ntiles) return;  // whole CTA exits together: nothing was started
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    // ---- one-time setup
+    for (int i = tid; i < C1; i += TC_THREADS)
+        w1s[i] = make_float4(__ldg(p.w1t + i), __ldg(p.w1t + C1 + i), __ldg(p.w1t + 2 * C1 + i), __ldg(p.b1 + i));
+    for (int i = tid; i < C2; i += TC_THREADS) b2s[i] = __ldg(p.b2 + i);
+    for (int i = tid; i < C3; i += TC_THREADS) b3s[i] = __ldg(p.b3 + i);
+    if (tid == 0) {
+        for (int i = 0; i < Cfg::NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < Cfg::KBMAX; ++i) mbar_init(&a_ready[i], 4);
+        mbar_init(acc2_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc3_full[i], 1); mbar_init(&acc3_empty[i], TC_COMPUTE_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == TC_COMPUTE_WARPS) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
+    const int4 *tiles = (const int4 *)p.tiles;
+
+    if (warp == TC_COMPUTE_WARPS + 1) {
+        // ================= weight loader (one elected lane) =================
+        if (lane == 0) {
+            const int ntile_loads = Cfg::RESIDENT ? 1 : my_tiles;
+            uint32_t job = 0;
+            for (int it = 0; it < ntile_loads; ++it) {
+                for (int j = 0; j < Cfg::JOBS; ++j, ++job) {
+                    const uint32_t st = job % Cfg::NSTAGE, ph = (job / Cfg::NSTAGE) & 1;
+                    mbar_wait(&w_empty[st], ph ^ 1);
+                    const bool l2 = j < Cfg::JOBS2;
+                    const uint32_t bytes = l2 ? Cfg::N2 * 128 : TC_STAGE_BYTES;
+                    const uint8_t *src = l2 ? (const uint8_t *)p.w2_tc + (size_t)j * (Cfg::N2 * 128)
+                                            : (const uint8_t *)p.w3_tc + (size_t)(j - Cfg::JOBS2) * TC_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&w_full[st], bytes);
+                    bulk_g2s(sW + st * TC_STAGE_BYTES, src, bytes, &w_full[st]);
+                }
+            }
+        }
+    } else if (warp == TC_COMPUTE_WARPS) {
+        // ================= MMA issuer (one elected lane) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc2 = make_idesc_tf32(128, Cfg::N2);
+            constexpr uint32_t idesc3 = make_idesc_tf32(128, Cfg::N3);
+            uint32_t job = 0, chunk = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                if (Cfg::RESIDENT) job = 0;
+                // ---- layer 2
+                for (int nc = 0; nc < Cfg::NCH2; ++nc) {
+                    for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
+                        const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
+                        if (nc == 0) mbar_wait(&a_ready[kb], 0);
+                        mbar_wait(&w_full[st], ph);
+                        tc_fence_after();
+                        const uint32_t a0 = sA_addr + kb * (TC_ROWS * 128), b0 = sW_addr + st * TC_STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_tf32(tmem_base + nc * Cfg::N2, make_desc_sw128(a0 + k * 32),
+                                     make_desc_sw128(b0 + k * 32), idesc2, (kb | k) != 0);
+                        if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
+                    }
+                }
+                mma_commit(acc2_full);
+                // ---- layer 3
+                for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
+                    const uint32_t buf = chunk & 1;
+                    mbar_wait(&acc3_empty[buf], ((chunk >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
+                        const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
+                        if (nc == 0) mbar_wait(&a_ready[kb], 1);
+                        mbar_wait(&w_full[st], ph);
+                        tc_fence_after();
+                        const uint32_t a0 = sA_addr + kb * (TC_ROWS * 128), b0 = sW_addr + st * TC_STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_tf32(tmem_base + 256 + buf * 128, make_desc_sw128(a0 + k * 32),
+                                     make_desc_sw128(b0 + k * 32), idesc3, (kb | k) != 0);
+                        if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
+                    }
+                    mma_commit(&acc3_full[buf]);
+                }
+            }
+        }
+    } else {
+        // ================= compute / epilogue warps =================
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const int rx = row & 7;
+        uint32_t chunk = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int4 td = tiles[tile];
+            const int b = td.x, row0 = td.y, nrows = td.z;
+            const float4 *grows = (const float4 *)p.rows + (size_t)b * p.row_cap + row0;
+            // staging buffers alternate with the tile parity: a warp that runs ahead into tile it+1
+            // must not overwrite what slower warps still read for tile it (they meet at this barrier)
+            float4 *recs = recs_all + (it & 1) * TC_ROWS;
+            int *sect_s = sect_all + (it & 1) * TC_ROWS;
+            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool valid = row < nrows;
+            if (h == 0) {
+                if (valid) rec = grows[row];
+                recs[row] = rec;
+                sect_s[row] = __float_as_int(rec.w) & 0x7fffffff;
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(TC_COMPUTE_WARPS * 32));
+            rec = recs[row];
+            const int sect = __float_as_int(rec.w) & 0x7fffffff;
+            // section bookkeeping of this warp's 32 rows (rows are section-sorted): bit r of endmask
+            // is set when row r is the last valid row of its section inside this warp
+            const int nsect = __shfl_down_sync(0xffffffffu, sect, 1);
+            const bool nvalid = (row + 1) < nrows;
+            const unsigned endmask = __ballot_sync(0xffffffffu, valid && (lane == 31 || !nvalid || nsect != sect));
+
+            // ---- layer 1 (fp32 FMA) -> A1, K-blocks kb = h, h+2, ...
+            for (int kb = h; kb < Cfg::KB1; kb += 2) {
+                uint8_t *dst = sA + kb * (TC_ROWS * 128) + row_off;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w = w1s[kb * 32 + c4 * 4 + j];
+                        o[j] = to_tf32(fmaxf(fmaf(rec.z, w.z, fmaf(rec.y, w.y, fmaf(rec.x, w.x, w.w))), 0.f));
+                    }
+                    *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[kb]);
+            }
+            // ---- epilogue 2: TMEM -> +bias, ReLU, TF32 -> A2 (same buffer; all layer-2 MMAs are done)
+            mbar_wait(acc2_full, it & 1);
+            tc_fence_after();
+            for (int kb = h; kb < Cfg::KB2; kb += 2) {
+                uint32_t v[32];
+                tmem_ld32(lane_taddr + kb * 32, v);
+                tmem_wait_ld();
+                uint8_t *dst = sA + kb * (TC_ROWS * 128) + row_off;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        o[j] = to_tf32(fmaxf(__uint_as_float(v[c4 * 4 + j]) + b2s[kb * 32 + c4 * 4 + j], 0.f));
+                    *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[kb]);
+            }
+            // ---- epilogue 3: per 128-column chunk: TMEM -> registers (thread = row), transpose 16-column
+            //      slabs through per-warp shared memory (thread = column), running max over the section's
+            //      rows, then +bias, ReLU and a coalesced integer atomicMax into the feature map
+            //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
+            int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
+            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * TC_SLAB_LD);
+            const int scol = lane & 15, srow0 = (lane >> 4) * 16;
+            for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
+                const uint32_t buf = chunk & 1;
+                mbar_wait(&acc3_full[buf], (chunk >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int col0 = h * 64 + half * 32;
+                    uint32_t v[32];
+                    tmem_ld32(lane_taddr + 256 + buf * 128 + col0, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4)
+                            *(uint4 *)(slab + lane * TC_SLAB_LD + c4 * 4) =
+                                make_uint4(v[sub * 16 + c4 * 4], v[sub * 16 + c4 * 4 + 1],
+                                           v[sub * 16 + c4 * 4 + 2], v[sub * 16 + c4 * 4 + 3]);
+                        __syncwarp();
+                        const int c = nc * Cfg::N3 + col0 + sub * 16 + scol;
+                        const float bias = b3s[c];
+                        float run = -INFINITY;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const int rr = srow0 + r;
+                            run = fmaxf(run, slab[rr * TC_SLAB_LD + scol]);
+                            if ((endmask >> rr) & 1u) {
+                                const float o = run + bias;
+                                if (o > 0.f)
+                                    atomicMax(feat + (size_t)sect_s[q * 32 + rr] * p.ld_feat + c, __float_as_int(o));
+                                run = -INFINITY;
+                            }
+                        }
+                        // lanes 0-15 may hold the partial max of a section that continues into rows
+                        // 16..31 (no end bit at row 15): flush it as a partial — atomic max merges halves
+                        if (srow0 == 0 && !((endmask >> 15) & 1u) && (q * 32 + 15) < nrows) {
+                            const float o = run + bias;
+                            if (o > 0.f)
+                                atomicMax(feat + (size_t)sect_s[q * 32 + 15] * p.ld_feat + c, __float_as_int(o));
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc3_empty[buf]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_COMPUTE_WARPS) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int C1, int C2, int C3>
+static int launch_tc(const fcn_pointnet_args &a, cudaStream_t stream) {
+    using Cfg = TcCfg<C1, C2, C3>;
+    auto kern = pointnet_tc_kernel<C1, C2, C3>;
+    FCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
+    int grid = sm_count();
+    if (grid > a.max_tiles) grid = a.max_tiles;
+    if (grid < 1) return FCN_OK;
+    kern<<<grid, TC_THREADS, Cfg::BYTES, stream>>>(a);
+    FCN_LAUNCH_CHECK();
+    return FCN_OK;
+}
+
+int pointnet_tiles_tc(const fcn_pointnet_args &a, cudaStream_t stream) {
+    FCN_REQUIRE(a.tile_rows == TC_ROWS, "the TF32 tensor-core variant needs tile_rows == 128");
+    FCN_REQUIRE(!a.unpooled, "the tensor-core variant only produces the pooled feature map");
+    FCN_REQUIRE(a.w2_tc && a.w3_tc, "NULL tensor-core weight image");
+    if (a.C1 == 64 && a.C2 == 64 && a.C3 == 128) return launch_tc<64, 64, 128>(a, stream);
+    if (a.C1 == 128 && a.C2 == 128 && a.C3 == 256) return launch_tc<128, 128, 256>(a, stream);
+    if (a.C1 == 256 && a.C2 == 256 && a.C3 == 512) return launch_tc<256, 256, 512>(a, stream);
+    return invalid("fcn_pointnet_tiles",
+                   "unsupported (C1,C2,C3); built: (64,64,128) (128,128,256) (256,256,512)");
+}
+
+}  // namespace fcn

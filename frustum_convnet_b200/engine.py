@@ -33,6 +33,25 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def tf32_rna(x: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to TF32 (10-bit mantissa), nearest with ties away from zero == cvt.rna.tf32.f32."""
+    i = x.contiguous().view(torch.int32)
+    mag = ((i & 0x7FFFFFFF) + 0x1000) & ~0x1FFF
+    return ((i & -0x80000000) | mag).view(torch.float32)
+
+
+def pack_sw128(w: torch.Tensor, n_chunk: int) -> torch.Tensor:
+    """(Cout, Cin) fp32 -> tensor-core stage images: for each n-chunk and each 32-wide K block a
+    [n_chunk rows][128 B] tile in the K-major 128-byte-swizzle layout (16-byte chunk c of row n
+    stored at chunk position c ^ (n & 7)), stages concatenated in consumption order (nc, kb)."""
+    co, ci = w.shape
+    assert co % n_chunk == 0 and ci % 32 == 0 and n_chunk % 8 == 0
+    x = tf32_rna(w.float()).view(co // n_chunk, n_chunk, ci // 32, 8, 4).permute(0, 2, 1, 3, 4)
+    n = torch.arange(n_chunk, device=w.device)
+    src = torch.arange(8, device=w.device)[None, :] ^ (n[:, None] & 7)          # [n][pos] -> source chunk
+    return x[:, :, n[:, None], src, :].contiguous().view(-1)
+
+
 def _fold_bn(sd, prefix) -> Tuple[torch.Tensor, torch.Tensor]:
     """(scale, shift) in float64 of an eval-mode BatchNorm (models/common.py:38-63 factories)."""
     g = sd[prefix + ".weight"].double()
@@ -90,8 +109,11 @@ class FrustumEngine:
             for j in (1, 2, 3):
                 w = sd["%s.conv%d.0.weight" % (p, j)].double()[:, :, 0, 0]      # (Co,Ci)
                 s, sh = _fold_bn(sd, "%s.conv%d.1" % (p, j))
-                lay["w%dt" % j] = (w * s[:, None]).t().contiguous().to(f32)     # (Ci,Co)
+                wf = (w * s[:, None]).to(f32)                                   # (Co,Ci) folded
+                lay["w%dt" % j] = wf.t().contiguous()                           # (Ci,Co)
                 lay["b%d" % j] = sh.to(f32).contiguous()
+                if self.precision == 1 and j >= 2:
+                    lay["w%d_tc" % j] = pack_sw128(wf, min(c2, 128) if j == 2 else 128)
             self.pn.append(lay)
         S, V = self.arch.num_scales, self.num_vec
         widths = (128, 256, 512, 512)[: S - 1]

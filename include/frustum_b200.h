@@ -154,6 +154,12 @@ FCN_API int fcn_decode_eval(int B, int T, int ld, int num_heading_bin, int num_s
 FCN_API int fcn_bct_to_btc(int B, int C, int T, int ld, const float *src, float *dst, fcn_stream_t stream);
 FCN_API int fcn_btc_to_bct(int B, int C, int T, int ld, const float *src, float *dst, fcn_stream_t stream);
 
+/* Self-test of the tcgen05/TMEM/bulk-copy building blocks: D (128,N) = A (128,K) * W^T with W given
+ * as the pre-swizzled stage image of the host packer (engine.pack_sw128).  N in {64,128},
+ * K multiple of 32 (<= 256).  Used by tests/ to pin the descriptor encodings on real hardware. */
+FCN_API int fcn_selftest_umma(int N, int K, const float *A, const void *w_img, float *D,
+                              fcn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+"""GPU: TF32 tensor-core (tcgen05) path.
+
+Tolerance: kind::tf32 keeps a 10-bit mantissa (operands rounded with cvt.rna, fp32 accumulate), the
+same arithmetic PyTorch/cuDNN use for convolutions by default on Ampere+ GPUs
+(torch.backends.cudnn.allow_tf32 = True).  Stated bound for the two tensor-core layers of a
+PointNet scale:  max|a-b| <= 4e-3 * max(1, max|ref|);  measured errors are printed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from test_gpu_parity import build_model, close, cuda_data, dev
+
+pytestmark = pytest.mark.gpu
+TF32_TOL = 4e-3
+
+
+@pytest.mark.parametrize("N,K", [(128, 32), (128, 64), (64, 64), (128, 256), (64, 128)])
+def test_umma_selftest_matches_fp64_matmul(N, K):
+    from frustum_convnet_b200 import _lib
+    from frustum_convnet_b200.engine import pack_sw128, tf32_rna
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    A = torch.randn(128, K, generator=g)
+    W = torch.randn(N, K, generator=g)
+    img = pack_sw128(W.to(dev()), N)
+    D = torch.full((128, N), float("nan"), device=dev())
+    Ad = A.to(dev()).contiguous()
+    _lib.call("fcn_selftest_umma", N, K, Ad.data_ptr(), img.data_ptr(), D.data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = tf32_rna(A).double() @ tf32_rna(W).double().t()
+    err = float((D.cpu().double() - ref).abs().max())
+    print("umma selftest N=%d K=%d max err %.3e" % (N, K, err))
+    assert err < 1e-3 * max(1.0, float(ref.abs().max())), err
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_pointnet_feat_tf32_matches_golden(name):
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    m.feat_net.precision = 1
+    d = cuda_data(data)
+    S = w["arch"].num_scales
+    feats = m.feat_net(d["point_cloud"], [d["center_ref%d" % (i + 1)] for i in range(S)], None, d["one_hot"])
+    for i, f in enumerate(feats):
+        ref = g["feat%d" % (i + 1)]
+        err = float(np.abs(f.cpu().numpy() - ref).max())
+        print("%s feat%d tf32 max err %.3e (max |ref| %.2f)" % (name, i + 1, err, np.abs(ref).max()))
+        close(f, ref, tol=TF32_TOL, what="%s feat%d tf32" % (name, i + 1))
+
+
+def test_tf32_full_size_car_b32_vs_fp32_path():
+    from frustum_convnet_b200 import config, synth
+    cfg, w = config.load_workload("car")
+    sd = synth.make_state_dict(w["arch"], 3, "KITTI", seed=21)
+    m0 = build_model(w, sd, cfg)
+    m1 = build_model(w, sd, cfg)
+    m1.precision = 1
+    data = synth.make_frustums("car", 32, seed=77)
+    d = cuda_data(data)
+    o0 = m0(d)
+    o1 = m1(d)
+    for j in (0, 1, 4, 5):
+        close(o1[j], o0[j], tol=TF32_TOL, what="tf32 vs fp32 out%d" % j)
+    o2 = m1(d)
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)      # deterministic (max-combine is order independent)
