@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 TF32_TOL = 4e-3
 
 
-@pytest.mark.parametrize("N,K", [(128, 32), (128, 64), (64, 64), (128, 256), (64, 128)])
+@pytest.mark.parametrize("N,K", [(128, 32), (128, 64), (64, 64), (128, 192), (64, 128), (64, 256)])
 def test_umma_selftest_matches_fp64_matmul(N, K):
     from frustum_convnet_b200 import _lib
     from frustum_convnet_b200.engine import pack_sw128, tf32_rna
