@@ -29,6 +29,7 @@ class GroupArgs(C.Structure):
         ("row_cap", C.c_int * MAX_SCALES), ("tile_cap", C.c_int * MAX_SCALES),
         ("rows", C.c_void_p * MAX_SCALES), ("cnt", C.c_void_p * MAX_SCALES),
         ("feat", C.c_void_p * MAX_SCALES), ("tiles", C.c_void_p * MAX_SCALES),
+        ("idx_scratch", C.c_void_p * MAX_SCALES),
         ("ntiles", C.c_void_p),
     ]
 

@@ -1,0 +1,214 @@
+// 1-D conv / transposed conv / 1x1 conv (+ folded BN, optional ReLU) as an implicit GEMM on the
+// 5th-gen tensor cores ("precision = 1"): tcgen05.mma kind::tf32, accumulator in TMEM, weights
+// staged by the TMA engine (bulk copies of pre-swizzled [N_TILE x 32] stage images), activations
+// gathered from the position-major maps by producer warps (taps / concat segments / zero padding),
+// rounded to TF32 (cvt.rna) and written straight into the K-major 128B-swizzled operand layout.
+// Same math as conv_gemm_simt.cu; replaces the Conv1d/DeConv1d/cat/head calls of
+// /root/reference/models/det_base.py:196-224,367-368.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace fcn {
+using namespace umma;
+
+constexpr int GT_ROWS = 128;
+constexpr int GT_PROD_WARPS = 4;                 // thread = output row (A producer, then epilogue)
+constexpr int GT_THREADS = (GT_PROD_WARPS + 2) * 32;
+constexpr int GT_NSTAGE = 4;
+
+template <int NT>
+struct GtCfg {
+    static constexpr int A_STAGE = GT_ROWS * 128, W_STAGE = NT * 128;
+    static constexpr int OFF_W = GT_NSTAGE * A_STAGE;
+    static constexpr int OFF_BAR = OFF_W + GT_NSTAGE * W_STAGE;
+    static constexpr int NBAR = 3 * GT_NSTAGE + 1;
+    static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+    static constexpr int BYTES = OFF_TMEM + 16 + 1024;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(GT_THREADS)
+conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
+    using Cfg = GtCfg<NT>;
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t *sA = smem, *sW = smem + Cfg::OFF_W;
+    uint64_t *bars = (uint64_t *)(smem + Cfg::OFF_BAR);
+    uint64_t *a_full = bars, *w_full = bars + GT_NSTAGE, *empty = bars + 2 * GT_NSTAGE;
+    uint64_t *acc_full = bars + 3 * GT_NSTAGE;
+    uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = p.B * p.T_out;
+    const int m0 = blockIdx.x * GT_ROWS, n_tile = blockIdx.y;
+    const int KB = p.K_pad / 32;
+
+    if (tid == 0) {
+        for (int i = 0; i < GT_NSTAGE; ++i) {
+            mbar_init(&a_full[i], GT_PROD_WARPS);
+            mbar_init(&w_full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == GT_PROD_WARPS) tmem_alloc<(NT < 32 ? 32 : NT)>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == GT_PROD_WARPS + 1) {
+        // ================= weight loader =================
+        if (lane == 0) {
+            const uint8_t *src = (const uint8_t *)p.w_tc + (size_t)n_tile * KB * Cfg::W_STAGE;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&w_full[st], Cfg::W_STAGE);
+                bulk_g2s(sW + st * Cfg::W_STAGE, src + (size_t)kb * Cfg::W_STAGE, Cfg::W_STAGE, &w_full[st]);
+            }
+        }
+    } else if (warp == GT_PROD_WARPS) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+            const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
+                mbar_wait(&a_full[st], ph);
+                mbar_wait(&w_full[st], ph);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    mma_tf32(tmem_base, make_desc_sw128(sA_addr + st * Cfg::A_STAGE + k * 32),
+                             make_desc_sw128(sW_addr + st * Cfg::W_STAGE + k * 32), idesc, (kb | k) != 0);
+                mma_commit(&empty[st]);
+            }
+            mma_commit(acc_full);
+        }
+    } else {
+        // ================= A producers (thread = row), then epilogue =================
+        const int row = warp * 32 + lane;
+        const int r = m0 + row;
+        const bool row_ok = r < M;
+        const int rb = row_ok ? r / p.T_out : 0;
+        const int rt = row_ok ? r - rb * p.T_out : 0;
+        const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const int rx = row & 7;
+
+        auto src_of = [&](int kb, bool &ok) -> const float4 * {
+            int seg = 0, c0 = kb * 32;
+#pragma unroll
+            for (int s = 0; s < FCN_MAX_SEGS; ++s)
+                if (s < p.n_seg - 1) {
+                    const int span = ((p.seg[s].C + 31) / 32) * 32;
+                    if (seg == s && c0 >= span) { c0 -= span; seg = s + 1; }
+                }
+            const fcn_conv_seg sg = p.seg[seg];
+            const int ts = rt * sg.stride + sg.tap;
+            ok = row_ok && ts >= 0 && ts < sg.T_src;
+            // channels [c0, c0+32) of the source row; columns >= ld are zero-filled per 16 B below
+            const float *base = sg.src + ((size_t)rb * sg.T_src + (ok ? ts : 0)) * sg.ld + c0;
+            return (const float4 *)base;
+        };
+        auto ld_limit = [&](int kb) -> int {  // number of valid float4 chunks (ld is a multiple of 4)
+            int seg = 0, c0 = kb * 32;
+#pragma unroll
+            for (int s = 0; s < FCN_MAX_SEGS; ++s)
+                if (s < p.n_seg - 1) {
+                    const int span = ((p.seg[s].C + 31) / 32) * 32;
+                    if (seg == s && c0 >= span) { c0 -= span; seg = s + 1; }
+                }
+            const int left = (p.seg[seg].ld - c0) / 4;
+            return left < 0 ? 0 : (left > 8 ? 8 : left);
+        };
+
+        float4 cur[8], nxt[8];
+        {
+            bool ok;
+            const float4 *s0 = src_of(0, ok);
+            const int lim = ld_limit(0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cur[c] = (ok && c < lim) ? __ldg(s0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int kb = 0; kb < KB; ++kb) {
+            const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
+            if (kb + 1 < KB) {  // prefetch the next K block while this one is converted and stored
+                bool ok;
+                const float4 *s1 = src_of(kb + 1, ok);
+                const int lim = ld_limit(kb + 1);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    nxt[c] = (ok && c < lim) ? __ldg(s1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_wait(&empty[st], ph ^ 1);
+            uint8_t *dst = sA + st * Cfg::A_STAGE + row_off;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *(float4 *)(dst + ((c ^ rx) << 4)) =
+                    make_float4(to_tf32(cur[c].x), to_tf32(cur[c].y), to_tf32(cur[c].z), to_tf32(cur[c].w));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[st]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+        }
+        // ---- epilogue: TMEM -> +bias (+ReLU) -> position-major global store
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_taddr + c0, v);
+            tmem_wait_ld();
+            const int n = n_tile * NT + c0;
+            if (!row_ok || n >= p.up * p.Cout) continue;
+            const int jj = n / p.Cout, co = n - jj * p.Cout;
+            const int tt = rt * p.up + jj;
+            if (tt >= p.T_store) continue;
+            float *out = p.out + ((size_t)rb * p.T_store + tt) * p.ld_out + p.c_off + co;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 bb = __ldg((const float4 *)(p.bias + n + c * 4));
+                float4 o = make_float4(__uint_as_float(v[c * 4]) + bb.x, __uint_as_float(v[c * 4 + 1]) + bb.y,
+                                       __uint_as_float(v[c * 4 + 2]) + bb.z, __uint_as_float(v[c * 4 + 3]) + bb.w);
+                if (p.relu) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                if (co + c * 4 < p.Cout) *(float4 *)(out + c * 4) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == GT_PROD_WARPS) {
+        tc_fence_after();
+        tmem_dealloc<(NT < 32 ? 32 : NT)>(tmem_base);
+    }
+}
+
+template <int NT>
+static int launch_gt(const fcn_conv_args &a, cudaStream_t stream) {
+    using Cfg = GtCfg<NT>;
+    auto kern = conv_gemm_tc_kernel<NT>;
+    FCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
+    const int M = a.B * a.T_out;
+    dim3 grid(ceil_div(M, GT_ROWS), a.n_cols / NT);
+    kern<<<grid, GT_THREADS, Cfg::BYTES, stream>>>(a);
+    FCN_LAUNCH_CHECK();
+    return FCN_OK;
+}
+
+// precision 1: N tile 128; precision 2: N tile 64 (more CTAs for the short, wide layers).
+int conv_gemm_tc(const fcn_conv_args &a, cudaStream_t stream) {
+    FCN_REQUIRE(a.w_tc != nullptr, "NULL tensor-core weight image");
+    FCN_REQUIRE(a.Cout % 32 == 0, "tensor-core variant needs Cout % 32 == 0");
+    if (a.B * a.T_out == 0) return FCN_OK;
+    if (a.precision == 2) return launch_gt<64>(a, stream);
+    FCN_REQUIRE(a.n_cols % 128 == 0, "n_cols must be a multiple of 128 for the 128-wide N tile");
+    return launch_gt<128>(a, stream);
+}
+
+}  // namespace fcn

@@ -74,51 +74,72 @@ qdp_kernel(int n, int m, float dis_z, int nsample, const float *__restrict__ xyz
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused grouping, two launches:
+//   group_count_kernel : grid (section chunks, S, B), one warp per section, 4 independent 32-point
+//                        ballots in flight per step; writes cnt (B,T) and the first min(hits,K) point
+//                        indices (int32 scratch, same order as the reference idx tensor).
+//   group_emit_kernel  : grid (B, S): block scan of cnt -> row offsets, tile table, zero-filled
+//                        feature block + one-hot channels, then one warp per section gathers
+//                        {x-cx, y-cy, z-cz, t} row records (no second scan of the cloud).
 struct GroupParams {
     fcn_group_args a;
 };
 
-constexpr int GROUP_THREADS = 512;
+constexpr int GC_WARPS = 8;            // sections per CTA in group_count_kernel
+constexpr int GE_THREADS = 256;
 
-__global__ void __launch_bounds__(GROUP_THREADS)
-group_rows_kernel(const __grid_constant__ GroupParams P) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(GC_WARPS * 32)
+group_count_kernel(const __grid_constant__ GroupParams P) {
+    extern __shared__ float sz[];        // z row of this frustum
+    const fcn_group_args &a = P.a;
+    const int b = blockIdx.z, s = blockIdx.y;
+    const int N = a.N, T = a.T[s], K = a.K[s];
+    const int t0 = blockIdx.x * GC_WARPS;
+    if (t0 >= T) return;
+    const float *pz = a.pc + (size_t)b * 3 * N + 2 * (size_t)N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sz[i] = __ldg(pz + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = t0 + warp;
+    if (t >= T) return;
+    const float dis_z = a.dis_z[s];
+    const float zc = __ldg(a.centers[s] + (size_t)b * 3 * T + 2 * (size_t)T + t);
+    int *out = a.idx_scratch[s] + ((size_t)b * T + t) * K;
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+    for (int base = 0; base < N && cnt < K; base += 128) {
+        bool hit[4];
+        unsigned m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = base + j * 32 + lane;
+            hit[j] = (k < N) && depth_hit(zc, sz[k < N ? k : 0], dis_z);
+            m[j] = __ballot_sync(0xffffffffu, hit[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pos = cnt + __popc(m[j] & lt);
+            if (hit[j] && pos < K) out[pos] = base + j * 32 + lane;
+            cnt += __popc(m[j]);
+        }
+    }
+    if (lane == 0) a.cnt[s][(size_t)b * T + t] = min(cnt, K);
+}
+
+__global__ void __launch_bounds__(GE_THREADS)
+group_emit_kernel(const __grid_constant__ GroupParams P) {
+    extern __shared__ int sm_i[];
     const fcn_group_args &a = P.a;
     const int b = blockIdx.x, s = blockIdx.y;
     const int N = a.N, T = a.T[s], K = a.K[s];
-    const float dis_z = a.dis_z[s];
-    float *sx = smem, *sy = sx + N, *sz = sy + N;
-    float *cz = sz + N;                      // T
-    int *scnt = (int *)(cz + T);             // T
-    int *sstart = scnt + T;                  // T
-    __shared__ int s_warp_tot[GROUP_THREADS / 32];
+    int *scnt = sm_i, *sstart = sm_i + T;
+    __shared__ int s_warp_tot[GE_THREADS / 32];
     __shared__ int s_carry, s_total, s_tile_base;
-
-    const float *pc = a.pc + (size_t)b * 3 * N;
-    const float *cen = a.centers[s] + (size_t)b * 3 * T;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        sx[i] = __ldg(pc + i);
-        sy[i] = __ldg(pc + N + i);
-        sz[i] = __ldg(pc + 2 * N + i);
-    }
-    for (int i = threadIdx.x; i < T; i += blockDim.x) cz[i] = __ldg(cen + 2 * T + i);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int *gcnt = a.cnt[s] + (size_t)b * T;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) scnt[i] = gcnt[i];
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    // pass 1: hit counts (capped at K)
-    for (int t = warp; t < T; t += nwarp) {
-        const float zc = cz[t];
-        int cnt = 0;
-        for (int base = 0; base < N && cnt < K; base += 32) {
-            const int k = base + lane;
-            const bool hit = (k < N) && depth_hit(zc, sz[k], dis_z);
-            cnt += __popc(__ballot_sync(0xffffffffu, hit));
-        }
-        if (lane == 0) scnt[t] = min(cnt, K);
-    }
-    __syncthreads();
-    // exclusive scan of rows-per-section over T (chunks of blockDim with a running carry)
     const bool uniq = a.unique_rows != 0;
     for (int base = 0; base < T; base += blockDim.x) {
         const int t = base + threadIdx.x;
@@ -148,7 +169,6 @@ group_rows_kernel(const __grid_constant__ GroupParams P) {
     }
     __syncthreads();
     const int total = s_total;
-    // tile table
     {
         int4 *tiles = (int4 *)a.tiles[s];
         const int nt = ceil_div(total, a.tile_rows);
@@ -158,61 +178,40 @@ group_rows_kernel(const __grid_constant__ GroupParams P) {
                 tiles[s_tile_base + i] = make_int4(b, row0, min(a.tile_rows, total - row0), 0);
         }
     }
-    // side outputs: cnt, zero-filled feature block + one-hot channels
-    {
-        int *gcnt = a.cnt[s] + (size_t)b * T;
-        for (int i = threadIdx.x; i < T; i += blockDim.x) gcnt[i] = scnt[i];
-        float *feat = a.feat[s];
-        if (feat != nullptr) {
-            const int ld = a.ld_feat[s], c3 = a.c3[s], V = a.num_vec;
-            float4 *f4 = (float4 *)(feat + (size_t)b * T * ld);
-            const int n4 = T * ld / 4;
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = threadIdx.x; i < n4; i += blockDim.x) f4[i] = z4;
-            __syncthreads();
-            if (a.one_hot != nullptr) {
-                float *fb = feat + (size_t)b * T * ld;
-                for (int i = threadIdx.x; i < T * V; i += blockDim.x) {
-                    const int t = i / V, v = i - t * V;
-                    fb[(size_t)t * ld + c3 + v] = __ldg(a.one_hot + (size_t)b * V + v);
-                }
+    float *feat = a.feat[s];
+    if (feat != nullptr) {
+        const int ld = a.ld_feat[s], c3 = a.c3[s], V = a.num_vec;
+        float4 *f4 = (float4 *)(feat + (size_t)b * T * ld);
+        const int n4 = T * ld / 4;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) f4[i] = z4;
+        __syncthreads();
+        if (a.one_hot != nullptr) {
+            float *fb = feat + (size_t)b * T * ld;
+            for (int i = threadIdx.x; i < T * V; i += blockDim.x) {
+                const int t = i / V, v = i - t * V;
+                fb[(size_t)t * ld + c3 + v] = __ldg(a.one_hot + (size_t)b * V + v);
             }
         }
     }
-    // pass 2: emit row records
+    // row records: one warp per section, lanes over the section's rows
+    const float *px = a.pc + (size_t)b * 3 * N, *py = px + N, *pz = py + N;
+    const float *cen = a.centers[s] + (size_t)b * 3 * T;
     float4 *rows = (float4 *)a.rows[s] + (size_t)b * a.row_cap[s];
-    const float *cx_g = cen, *cy_g = cen + T;
+    const int *gidx = a.idx_scratch[s] + (size_t)b * T * K;
     for (int t = warp; t < T; t += nwarp) {
-        const float zc = cz[t];
-        const float cx = __ldg(cx_g + t), cy = __ldg(cy_g + t);
         const int c = scnt[t];
+        if (c == 0 && uniq) continue;
+        const float cx = __ldg(cen + t), cy = __ldg(cen + T + t), cz = __ldg(cen + 2 * T + t);
         float4 *out = rows + sstart[t];
-        if (c == 0) {
-            if (!uniq) {  // masked section: K rows gathering point 0 (zero-initialised idx), flagged
-                const float4 r = make_float4(__fsub_rn(sx[0], cx), __fsub_rn(sy[0], cy),
-                                             __fsub_rn(sz[0], zc), __int_as_float(t | 0x80000000));
-                for (int l = lane; l < K; l += 32) out[l] = r;
-            }
-            continue;
-        }
-        int cnt = 0, first = 0;
-        for (int base = 0; base < N && cnt < K; base += 32) {
-            const int k = base + lane;
-            const bool hit = (k < N) && depth_hit(zc, sz[k], dis_z);
-            const unsigned mask = __ballot_sync(0xffffffffu, hit);
-            if (mask) {
-                if (cnt == 0) first = base + __ffs(mask) - 1;
-                const int pos = cnt + __popc(mask & ((1u << lane) - 1));
-                if (hit && pos < K)
-                    out[pos] = make_float4(__fsub_rn(sx[k], cx), __fsub_rn(sy[k], cy),
-                                           __fsub_rn(sz[k], zc), __int_as_float(t));
-                cnt += __popc(mask);
-            }
-        }
-        if (!uniq) {
-            const float4 r = make_float4(__fsub_rn(sx[first], cx), __fsub_rn(sy[first], cy),
-                                         __fsub_rn(sz[first], zc), __int_as_float(t));
-            for (int l = c + lane; l < K; l += 32) out[l] = r;
+        const int *ix = gidx + (size_t)t * K;
+        const int nrow = uniq ? c : K;
+        const int first = c > 0 ? ix[0] : 0;      // back-fill source (cu:55-59); masked rows use point 0
+        const int tag = c > 0 ? t : (t | 0x80000000);
+        for (int l = lane; l < nrow; l += 32) {
+            const int k = l < c ? ix[l] : first;
+            out[l] = make_float4(__fsub_rn(__ldg(px + k), cx), __fsub_rn(__ldg(py + k), cy),
+                                 __fsub_rn(__ldg(pz + k), cz), __int_as_float(tag));
         }
     }
 }
@@ -272,15 +271,21 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
         FCN_REQUIRE(a.feat[s] == nullptr || a.ld_feat[s] >= a.c3[s] + a.num_vec, "ld_feat too small");
         maxT = a.T[s] > maxT ? a.T[s] : maxT;
     }
-    const size_t smem = sizeof(float) * (3 * (size_t)a.N + 3 * (size_t)maxT);
-    FCN_REQUIRE(smem <= 200 * 1024, "N/T too large for the shared-memory staging");
+    for (int s = 0; s < a.num_scales; ++s) FCN_REQUIRE(a.idx_scratch[s] != nullptr, "NULL idx_scratch");
+    const size_t smem_c = sizeof(float) * (size_t)a.N, smem_e = sizeof(int) * 2 * (size_t)maxT;
+    FCN_REQUIRE(smem_c <= 200 * 1024 && smem_e <= 200 * 1024, "N/T too large for the shared-memory staging");
+    FCN_REQUIRE(a.B <= 65535 && a.num_scales <= 65535, "grid too large");
     GroupParams P;
     P.a = a;
-    if (smem > 48 * 1024)
-        FCN_CUDA(cudaFuncSetAttribute(group_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    dim3 grid(a.B, a.num_scales);
-    group_rows_kernel<<<grid, GROUP_THREADS, smem, (cudaStream_t)stream>>>(P);
+    if (smem_c > 48 * 1024)
+        FCN_CUDA(cudaFuncSetAttribute(group_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    if (smem_e > 48 * 1024)
+        FCN_CUDA(cudaFuncSetAttribute(group_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    dim3 gc(ceil_div(maxT, GC_WARPS), a.num_scales, a.B);
+    group_count_kernel<<<gc, GC_WARPS * 32, smem_c, (cudaStream_t)stream>>>(P);
+    FCN_LAUNCH_CHECK();
+    dim3 ge(a.B, a.num_scales);
+    group_emit_kernel<<<ge, GE_THREADS, smem_e, (cudaStream_t)stream>>>(P);
     FCN_LAUNCH_CHECK();
     return FCN_OK;
 }

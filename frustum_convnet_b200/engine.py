@@ -69,6 +69,13 @@ class _ConvLayer:
         self.name, self.segs, self.K_pad, self.n_cols = name, segs, K_pad, n_cols
         self.Cout, self.up, self.relu, self.wt, self.bias = Cout, up, relu, wt, bias
         self.out, self.c_off = out, c_off
+        self._tc = {}
+
+    def tc_image(self, n_tile: int) -> torch.Tensor:
+        """Pre-swizzled tensor-core stage images [n_tile][kb][n_tile rows x 128 B] (lazy, cached)."""
+        if n_tile not in self._tc:
+            self._tc[n_tile] = pack_sw128(self.wt.t().contiguous(), n_tile)
+        return self._tc[n_tile]
 
 
 class FrustumEngine:
@@ -243,11 +250,12 @@ class _Plan:
         K = arch.nsample
         tr = eng.tile_rows
         self.buf: Dict[str, torch.Tensor] = {}
-        self.rows, self.cnt, self.tiles, self.max_tiles = [], [], [], []
+        self.rows, self.cnt, self.tiles, self.max_tiles, self.idx32 = [], [], [], [], []
         for s in range(S):
             cap = T[s] * K[s]
             self.rows.append(torch.empty((B, cap, 4), dtype=f32, device=dev))
             self.cnt.append(torch.empty((B, T[s]), dtype=torch.int32, device=dev))
+            self.idx32.append(torch.empty((B, T[s], K[s]), dtype=torch.int32, device=dev))
             mt = B * ((cap + tr - 1) // tr)
             self.max_tiles.append(mt)
             self.tiles.append(torch.empty((max(mt, 1), 4), dtype=torch.int32, device=dev))
@@ -293,6 +301,7 @@ class _Plan:
             g.tile_cap[s] = max(self.max_tiles[s], 1)
             g.rows[s], g.cnt[s] = _ptr(self.rows[s]), _ptr(self.cnt[s])
             g.feat[s], g.tiles[s] = _ptr(self.buf["feat%d" % (s + 1)]), _ptr(self.tiles[s])
+            g.idx_scratch[s] = _ptr(self.idx32[s])
         g.ntiles = _ptr(self.ntiles)
         self.group_args = g
         self.pn_args = []
@@ -325,8 +334,14 @@ class _Plan:
                 a.seg[j].src, a.seg[j].ld, a.seg[j].C = _ptr(t), t.shape[2], c
                 a.seg[j].T_src, a.seg[j].tap, a.seg[j].stride = t.shape[1], tap, st
             a.K_pad, a.n_cols, a.Cout, a.up, a.relu = L.K_pad, L.n_cols, L.Cout, L.up, L.relu
-            a.precision = 0
-            a.wt, a.bias, a.w_tc = _ptr(L.wt), _ptr(L.bias), None
+            a.precision, a.w_tc = 0, None
+            if eng.precision == 1 and L.Cout % 32 == 0:
+                # N tile 128 when that already gives enough CTAs, else 64 (more, smaller tiles)
+                m_tiles = (a.B * a.T_out + 127) // 128
+                nt = 128 if (L.n_cols % 128 == 0 and m_tiles * (L.n_cols // 128) >= 96) else 64
+                a.precision = 1 if nt == 128 else 2
+                a.w_tc = _ptr(L.tc_image(nt))
+            a.wt, a.bias = _ptr(L.wt), _ptr(L.bias)
             a.out, a.ld_out, a.T_store, a.c_off = _ptr(out), out.shape[2], out.shape[1], L.c_off
             self.conv_args.append(a)
 
@@ -488,7 +503,7 @@ class _Plan:
         kern.append(dict(name="decode_eval", ms=float(acc[-1]), executed_gflop=0.0, nominal_gflop=0.0))
         for k_ in kern:
             k_["executed_tflops"] = k_["executed_gflop"] / max(k_["ms"], 1e-9)  # GFLOP/ms == TFLOP/s
-        return dict(kernels=kern, launches_per_step=len(names),
+        return dict(kernels=kern, launches_per_step=len(names) + 1,   # group_rows = count + emit kernels
                     unique_row_fraction=float(sum(rows_exec)) / float(max(sum(rows_nom), 1)))
 
     def logits(self):
@@ -518,6 +533,8 @@ def _run_module(eng: FrustumEngine, scale: int, pc, new_pc):
         g.centers[0], g.T[0], g.K[0], g.dis_z[0] = _ptr(new_pc), T, K, eng.dists[scale]
         g.c3[0], g.ld_feat[0], g.row_cap[0], g.tile_cap[0] = c3, 0, T * K, max(mt, 1)
         g.rows[0], g.cnt[0], g.feat[0], g.tiles[0] = _ptr(rows), _ptr(cnt), None, _ptr(tiles)
+        idx32 = torch.empty((B, T, K), dtype=torch.int32, device=dev)
+        g.idx_scratch[0] = _ptr(idx32)
         g.ntiles = _ptr(ntiles)
         st = _stream()
         _lib.call("fcn_group_rows", C.byref(g), st)

@@ -71,6 +71,7 @@ FCN_API int fcn_query_depth_point_b3n(int b, int n, int m, float dis_z, int nsam
  *     rows are appended to tiles[s] (int4 {b, row0, nrows, 0}) and counted in ntiles[s].
  *     Side outputs: cnt[s] (B,T_s) int32; feat[s] (B,T_s,ld_feat[s]) fp32 position-major is
  *     zero-filled and its one-hot channels [c3[s], c3[s]+num_vec) are written (det_base.py:145-157).
+ *     idx_scratch[s] receives the selected point indices (the valid prefix of the reference idx).
  *     `ntiles` (int32[FCN_MAX_SCALES]) must be zero before the call (cudaMemsetAsync by caller).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -87,6 +88,7 @@ typedef struct {
     int32_t *cnt[FCN_MAX_SCALES];           /* (B,T_s) */
     float *feat[FCN_MAX_SCALES];            /* (B,T_s,ld_feat) or NULL */
     void *tiles[FCN_MAX_SCALES];            /* int4[tile_cap] */
+    int32_t *idx_scratch[FCN_MAX_SCALES];   /* (B,T_s,K_s) int32: first min(hits,K) point indices */
     int32_t *ntiles;                        /* int32[FCN_MAX_SCALES] */
 } fcn_group_args;
 FCN_API int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream);

@@ -50,6 +50,33 @@ def test_pointnet_feat_tf32_matches_golden(name):
         close(f, ref, tol=TF32_TOL, what="%s feat%d tf32" % (name, i + 1))
 
 
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_conv_feat_net_and_forward_tf32_match_golden(name):
+    """FCN on tensor cores: up to 11 chained TF32 GEMMs -> stated bound 1e-2 * max|ref|."""
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    m.conv_net.precision = 1
+    S = w["arch"].num_scales
+    feats = [torch.from_numpy(g["feat%d" % (i + 1)]).to(dev()) for i in range(S)]
+    x = m.conv_net(*feats)
+    err = float(np.abs(x.cpu().numpy() - g["x"]).max())
+    print("%s conv_net tf32 max err %.3e (max |ref| %.2f)" % (name, err, np.abs(g["x"]).max()))
+    close(x, g["x"], tol=1e-2, what=name + " conv_net tf32")
+    m.precision = 1
+    out = m(cuda_data(data))
+    B = data["point_cloud"].shape[0]
+    plan = m.engine().plan(B, data["point_cloud"].shape[2],
+                           [data["center_ref%d" % (i + 1)].shape[2] for i in range(S)])
+    cls, reg = plan.logits()
+    for nm, t, ref in (("cls", cls.view(B, -1, 2).permute(0, 2, 1), g["cls"]),
+                       ("reg", reg.view(B, -1, reg.shape[1]).permute(0, 2, 1), g["reg"])):
+        err = float(np.abs(t.cpu().numpy() - ref).max())
+        print("%s %s logits tf32 max err %.3e (max |ref| %.2f)" % (name, nm, err, np.abs(ref).max()))
+        close(t, ref, tol=1e-2, what=name + " " + nm + " tf32")
+    close(out[0], g["out0"], tol=1e-2, what="cls_probs tf32")
+    close(out[1], g["out1"], tol=1e-2, what="center tf32")
+
+
 def test_tf32_full_size_car_b32_vs_fp32_path():
     from frustum_convnet_b200 import config, synth
     cfg, w = config.load_workload("car")
@@ -62,7 +89,7 @@ def test_tf32_full_size_car_b32_vs_fp32_path():
     o0 = m0(d)
     o1 = m1(d)
     for j in (0, 1, 4, 5):
-        close(o1[j], o0[j], tol=TF32_TOL, what="tf32 vs fp32 out%d" % j)
+        close(o1[j], o0[j], tol=1e-2, what="tf32 vs fp32 out%d" % j)
     o2 = m1(d)
     for a, b in zip(o1, o2):
         assert torch.equal(a, b)      # deterministic (max-combine is order independent)
