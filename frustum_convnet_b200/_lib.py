@@ -61,7 +61,7 @@ class ConvArgs(C.Structure):
         ("relu", C.c_int), ("precision", C.c_int),
         ("wt", C.c_void_p), ("bias", C.c_void_p), ("w_tc", C.c_void_p),
         ("out", C.c_void_p),
-        ("ld_out", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int),
+        ("ld_out", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int), ("round_out", C.c_int),
     ]
 
 

@@ -1,8 +1,11 @@
 // 1-D conv / transposed conv / 1x1 conv (+ folded BN, optional ReLU) as an implicit GEMM on the
 // 5th-gen tensor cores ("precision = 1"): tcgen05.mma kind::tf32, accumulator in TMEM, weights
 // staged by the TMA engine (bulk copies of pre-swizzled [N_TILE x 32] stage images), activations
-// gathered from the position-major maps by producer warps (taps / concat segments / zero padding),
-// rounded to TF32 (cvt.rna) and written straight into the K-major 128B-swizzled operand layout.
+// gathered from the position-major maps (taps / concat segments / zero padding) with 16-byte
+// cp.async (LDGSTS, zero-fill) issued by one thread per output row straight into the K-major
+// 128B-swizzled operand layout — no register staging, NSTAGE K blocks in flight.  Activations in
+// HBM are already TF32-rounded by their producers (cvt.rna in the epilogues, `round_out`), so the
+// tensor core's operand truncation is exact.
 // Same math as conv_gemm_simt.cu; replaces the Conv1d/DeConv1d/cat/head calls of
 // /root/reference/models/det_base.py:196-224,367-368.
 #include "common.cuh"
@@ -14,7 +17,7 @@ using namespace umma;
 constexpr int GT_ROWS = 128;
 constexpr int GT_PROD_WARPS = 4;                 // thread = output row (A producer, then epilogue)
 constexpr int GT_THREADS = (GT_PROD_WARPS + 2) * 32;
-constexpr int GT_NSTAGE = 4;
+constexpr int GT_NSTAGE = 6;
 
 template <int NT>
 struct GtCfg {
@@ -45,7 +48,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
 
     if (tid == 0) {
         for (int i = 0; i < GT_NSTAGE; ++i) {
-            mbar_init(&a_full[i], GT_PROD_WARPS);
+            mbar_init(&a_full[i], GT_PROD_WARPS * 32);
             mbar_init(&w_full[i], 1);
             mbar_init(&empty[i], 1);
         }
@@ -78,6 +81,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
                 const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
                 mbar_wait(&a_full[st], ph);
                 mbar_wait(&w_full[st], ph);
+                fence_proxy_async();   // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -97,62 +101,28 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
         const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const int rx = row & 7;
 
-        auto src_of = [&](int kb, bool &ok) -> const float4 * {
-            int seg = 0, c0 = kb * 32;
-#pragma unroll
-            for (int s = 0; s < FCN_MAX_SEGS; ++s)
-                if (s < p.n_seg - 1) {
-                    const int span = ((p.seg[s].C + 31) / 32) * 32;
-                    if (seg == s && c0 >= span) { c0 -= span; seg = s + 1; }
-                }
-            const fcn_conv_seg sg = p.seg[seg];
-            const int ts = rt * sg.stride + sg.tap;
-            ok = row_ok && ts >= 0 && ts < sg.T_src;
-            // channels [c0, c0+32) of the source row; columns >= ld are zero-filled per 16 B below
-            const float *base = sg.src + ((size_t)rb * sg.T_src + (ok ? ts : 0)) * sg.ld + c0;
-            return (const float4 *)base;
-        };
-        auto ld_limit = [&](int kb) -> int {  // number of valid float4 chunks (ld is a multiple of 4)
-            int seg = 0, c0 = kb * 32;
-#pragma unroll
-            for (int s = 0; s < FCN_MAX_SEGS; ++s)
-                if (s < p.n_seg - 1) {
-                    const int span = ((p.seg[s].C + 31) / 32) * 32;
-                    if (seg == s && c0 >= span) { c0 -= span; seg = s + 1; }
-                }
-            const int left = (p.seg[seg].ld - c0) / 4;
-            return left < 0 ? 0 : (left > 8 ? 8 : left);
-        };
-
-        float4 cur[8], nxt[8];
-        {
-            bool ok;
-            const float4 *s0 = src_of(0, ok);
-            const int lim = ld_limit(0);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) cur[c] = (ok && c < lim) ? __ldg(s0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const uint32_t sA_row = smem_u32(sA) + row_off;
+        int seg = 0, seg_c0 = 0;   // running (segment, channel offset) of the current K block
         for (int kb = 0; kb < KB; ++kb) {
             const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
-            if (kb + 1 < KB) {  // prefetch the next K block while this one is converted and stored
-                bool ok;
-                const float4 *s1 = src_of(kb + 1, ok);
-                const int lim = ld_limit(kb + 1);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    nxt[c] = (ok && c < lim) ? __ldg(s1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            const fcn_conv_seg sg = p.seg[seg];
+            const int ts = rt * sg.stride + sg.tap;
+            const bool ok = row_ok && ts >= 0 && ts < sg.T_src;
+            const float *src = sg.src + ((size_t)rb * sg.T_src + (ok ? ts : 0)) * sg.ld + seg_c0;
+            const int lim = ok ? (sg.ld - seg_c0) / 4 : 0;     // valid 16-byte chunks of this row
             mbar_wait(&empty[st], ph ^ 1);
-            uint8_t *dst = sA + st * Cfg::A_STAGE + row_off;
+            const uint32_t dst = sA_row + st * Cfg::A_STAGE;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *(float4 *)(dst + ((c ^ rx) << 4)) =
-                    make_float4(to_tf32(cur[c].x), to_tf32(cur[c].y), to_tf32(cur[c].z), to_tf32(cur[c].w));
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[st]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+            for (int c = 0; c < 8; ++c) {
+                const int sz = c < lim ? 16 : 0;               // src-size 0 -> 16 bytes of zeros
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + ((c ^ rx) << 4)),
+                             "l"(src + (c < lim ? c * 4 : 0)), "r"(sz)
+                             : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&a_full[st]))
+                         : "memory");
+            seg_c0 += 32;
+            if (seg_c0 >= ((sg.C + 31) / 32) * 32) { seg_c0 = 0; ++seg; if (seg >= p.n_seg) seg = p.n_seg - 1; }
         }
         // ---- epilogue: TMEM -> +bias (+ReLU) -> position-major global store
         mbar_wait(acc_full, 0);
@@ -177,7 +147,8 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
                 if (p.relu) {
                     o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                 }
-                if (co + c * 4 < p.Cout) *(float4 *)(out + c * 4) = o;
+                if (p.round_out) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
+                *(float4 *)(out + c * 4) = o;
             }
         }
     }

@@ -85,22 +85,28 @@ struct GroupParams {
     fcn_group_args a;
 };
 
-constexpr int GC_WARPS = 8;            // sections per CTA in group_count_kernel
-constexpr int GE_THREADS = 256;
+constexpr int GC_WARPS = 32;           // sections per CTA in group_count_kernel
+constexpr int GE_THREADS = 512;
 
 __global__ void __launch_bounds__(GC_WARPS * 32)
 group_count_kernel(const __grid_constant__ GroupParams P) {
     extern __shared__ float sz[];        // z row of this frustum
     const fcn_group_args &a = P.a;
-    const int b = blockIdx.z, s = blockIdx.y;
+    const int b = blockIdx.y;
+    // blockIdx.x enumerates (scale, 32-section chunk) pairs
+    int s = 0, chunk = blockIdx.x;
+    for (; s < a.num_scales; ++s) {
+        const int nc = ceil_div(a.T[s], GC_WARPS);
+        if (chunk < nc) break;
+        chunk -= nc;
+    }
+    if (s >= a.num_scales) return;
     const int N = a.N, T = a.T[s], K = a.K[s];
-    const int t0 = blockIdx.x * GC_WARPS;
-    if (t0 >= T) return;
     const float *pz = a.pc + (size_t)b * 3 * N + 2 * (size_t)N;
     for (int i = threadIdx.x; i < N; i += blockDim.x) sz[i] = __ldg(pz + i);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = t0 + warp;
+    const int t = chunk * GC_WARPS + warp;
     if (t >= T) return;
     const float dis_z = a.dis_z[s];
     const float zc = __ldg(a.centers[s] + (size_t)b * 3 * T + 2 * (size_t)T + t);
@@ -133,11 +139,16 @@ group_emit_kernel(const __grid_constant__ GroupParams P) {
     const int b = blockIdx.x, s = blockIdx.y;
     const int N = a.N, T = a.T[s], K = a.K[s];
     int *scnt = sm_i, *sstart = sm_i + T;
+    float *scen = (float *)(sm_i + 2 * T);     // 3T: section centres (x | y | z)
     __shared__ int s_warp_tot[GE_THREADS / 32];
     __shared__ int s_carry, s_total, s_tile_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int *gcnt = a.cnt[s] + (size_t)b * T;
     for (int i = threadIdx.x; i < T; i += blockDim.x) scnt[i] = gcnt[i];
+    {
+        const float *cen_g = a.centers[s] + (size_t)b * 3 * T;
+        for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) scen[i] = __ldg(cen_g + i);
+    }
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const bool uniq = a.unique_rows != 0;
@@ -194,25 +205,30 @@ group_emit_kernel(const __grid_constant__ GroupParams P) {
             }
         }
     }
-    // row records: one warp per section, lanes over the section's rows
+    // row records, one thread per row (independent gathers -> latency overlapped)
     const float *px = a.pc + (size_t)b * 3 * N, *py = px + N, *pz = py + N;
-    const float *cen = a.centers[s] + (size_t)b * 3 * T;
     float4 *rows = (float4 *)a.rows[s] + (size_t)b * a.row_cap[s];
     const int *gidx = a.idx_scratch[s] + (size_t)b * T * K;
-    for (int t = warp; t < T; t += nwarp) {
-        const int c = scnt[t];
-        if (c == 0 && uniq) continue;
-        const float cx = __ldg(cen + t), cy = __ldg(cen + T + t), cz = __ldg(cen + 2 * T + t);
-        float4 *out = rows + sstart[t];
-        const int *ix = gidx + (size_t)t * K;
-        const int nrow = uniq ? c : K;
-        const int first = c > 0 ? ix[0] : 0;      // back-fill source (cu:55-59); masked rows use point 0
-        const int tag = c > 0 ? t : (t | 0x80000000);
-        for (int l = lane; l < nrow; l += 32) {
-            const int k = l < c ? ix[l] : first;
-            out[l] = make_float4(__fsub_rn(__ldg(px + k), cx), __fsub_rn(__ldg(py + k), cy),
-                                 __fsub_rn(__ldg(pz + k), cz), __int_as_float(tag));
+    const int nrows_total = uniq ? total : T * K;
+    for (int i = threadIdx.x; i < nrows_total; i += blockDim.x) {
+        int t, l;
+        if (uniq) {   // upper_bound over the exclusive offsets: last t with sstart[t] <= i and cnt > 0
+            int lo = 0, hi = T - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (sstart[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            t = lo;
+            l = i - sstart[t];
+        } else {
+            t = i / K;
+            l = i - t * K;
         }
+        const int c = scnt[t];
+        const int k = c > 0 ? gidx[(size_t)t * K + (l < c ? l : 0)] : 0;   // back-fill: first hit (cu:55-59)
+        const int tag = c > 0 ? t : (t | 0x80000000);
+        rows[i] = make_float4(__fsub_rn(__ldg(px + k), scen[t]), __fsub_rn(__ldg(py + k), scen[T + t]),
+                              __fsub_rn(__ldg(pz + k), scen[2 * T + t]), __int_as_float(tag));
     }
 }
 
@@ -272,7 +288,7 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
         maxT = a.T[s] > maxT ? a.T[s] : maxT;
     }
     for (int s = 0; s < a.num_scales; ++s) FCN_REQUIRE(a.idx_scratch[s] != nullptr, "NULL idx_scratch");
-    const size_t smem_c = sizeof(float) * (size_t)a.N, smem_e = sizeof(int) * 2 * (size_t)maxT;
+    const size_t smem_c = sizeof(float) * (size_t)a.N, smem_e = sizeof(int) * 5 * (size_t)maxT;
     FCN_REQUIRE(smem_c <= 200 * 1024 && smem_e <= 200 * 1024, "N/T too large for the shared-memory staging");
     FCN_REQUIRE(a.B <= 65535 && a.num_scales <= 65535, "grid too large");
     GroupParams P;
@@ -281,7 +297,9 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
         FCN_CUDA(cudaFuncSetAttribute(group_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     if (smem_e > 48 * 1024)
         FCN_CUDA(cudaFuncSetAttribute(group_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-    dim3 gc(ceil_div(maxT, GC_WARPS), a.num_scales, a.B);
+    int nchunks = 0;
+    for (int s = 0; s < a.num_scales; ++s) nchunks += ceil_div(a.T[s], GC_WARPS);
+    dim3 gc(nchunks, a.B);
     group_count_kernel<<<gc, GC_WARPS * 32, smem_c, (cudaStream_t)stream>>>(P);
     FCN_LAUNCH_CHECK();
     dim3 ge(a.B, a.num_scales);

@@ -264,7 +264,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                             const int rr = srow0 + r;
                             run = fmaxf(run, slab[rr * TC_SLAB_LD + scol]);
                             if ((endmask >> rr) & 1u) {
-                                const float o = run + bias;
+                                const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
                                 if (o > 0.f)
                                     atomicMax(feat + (size_t)sect_s[q * 32 + rr] * p.ld_feat + c, __float_as_int(o));
                                 run = -INFINITY;
@@ -273,7 +273,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         // lanes 0-15 may hold the partial max of a section that continues into rows
                         // 16..31 (no end bit at row 15): flush it as a partial — atomic max merges halves
                         if (srow0 == 0 && !((endmask >> 15) & 1u) && (q * 32 + 15) < nrows) {
-                            const float o = run + bias;
+                            const float o = to_tf32(run + bias);
                             if (o > 0.f)
                                 atomicMax(feat + (size_t)sect_s[q * 32 + 15] * p.ld_feat + c, __float_as_int(o));
                         }

@@ -341,6 +341,7 @@ class _Plan:
                 nt = 128 if (L.n_cols % 128 == 0 and m_tiles * (L.n_cols // 128) >= 96) else 64
                 a.precision = 1 if nt == 128 else 2
                 a.w_tc = _ptr(L.tc_image(nt))
+            a.round_out = 1 if (eng.precision == 1 and L.name != "heads") else 0
             a.wt, a.bias = _ptr(L.wt), _ptr(L.bias)
             a.out, a.ld_out, a.T_store, a.c_off = _ptr(out), out.shape[2], out.shape[1], L.c_off
             self.conv_args.append(a)

@@ -138,6 +138,7 @@ typedef struct {
     const void *w_tc;
     float *out;
     int ld_out, T_store, c_off;
+    int round_out;   /* 1: round outputs to TF32 (cvt.rna) because a tensor-core GEMM consumes them */
 } fcn_conv_args;
 FCN_API int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream);
 
