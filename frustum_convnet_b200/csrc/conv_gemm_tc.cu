@@ -98,25 +98,38 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
         const bool row_ok = r < M;
         const int rb = row_ok ? r / p.T_out : 0;
         const int rt = row_ok ? r - rb * p.T_out : 0;
-        const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-        const int rx = row & 7;
 
-        const uint32_t sA_row = smem_u32(sA) + row_off;
+        // Coalesced gather: one warp instruction covers 4 rows x 128 B (lane -> row j*4 + lane/8,
+        // 16-byte chunk lane%8), i.e. 4 full cache lines instead of 32 partial ones.
+        const int chunk = lane & 7;
+        int gb[8], gt[8];               // (frustum, position) of the 8 rows this lane feeds
+        uint32_t gdst[8];
+        unsigned gok = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int lr = warp * 32 + j * 4 + (lane >> 3);
+            const int gr = m0 + lr;
+            const bool okr = gr < M;
+            gb[j] = okr ? gr / p.T_out : 0;
+            gt[j] = okr ? gr - gb[j] * p.T_out : 0;
+            gok |= (okr ? 1u : 0u) << j;
+            gdst[j] = smem_u32(sA) + (uint32_t)((lr >> 3) * 1024 + (lr & 7) * 128 + ((chunk ^ (lr & 7)) << 4));
+        }
         int seg = 0, seg_c0 = 0;   // running (segment, channel offset) of the current K block
         for (int kb = 0; kb < KB; ++kb) {
             const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
             const fcn_conv_seg sg = p.seg[seg];
-            const int ts = rt * sg.stride + sg.tap;
-            const bool ok = row_ok && ts >= 0 && ts < sg.T_src;
-            const float *src = sg.src + ((size_t)rb * sg.T_src + (ok ? ts : 0)) * sg.ld + seg_c0;
-            const int lim = ok ? (sg.ld - seg_c0) / 4 : 0;     // valid 16-byte chunks of this row
+            const int ch = seg_c0 + chunk * 4;
+            const bool ch_ok = ch < sg.ld;                     // ld is a multiple of 4; pad columns are zero
             mbar_wait(&empty[st], ph ^ 1);
-            const uint32_t dst = sA_row + st * Cfg::A_STAGE;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int sz = c < lim ? 16 : 0;               // src-size 0 -> 16 bytes of zeros
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + ((c ^ rx) << 4)),
-                             "l"(src + (c < lim ? c * 4 : 0)), "r"(sz)
+            for (int j = 0; j < 8; ++j) {
+                const int ts = gt[j] * sg.stride + sg.tap;
+                const bool ok = ch_ok && ((gok >> j) & 1u) && ts >= 0 && ts < sg.T_src;
+                const float *src = ok ? sg.src + ((size_t)gb[j] * sg.T_src + ts) * sg.ld + ch : sg.src;
+                const int sz = ok ? 16 : 0;                    // src-size 0 -> 16 bytes of zeros
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(gdst[j] + st * Cfg::A_STAGE),
+                             "l"(src), "r"(sz)
                              : "memory");
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&a_full[st]))

@@ -22,7 +22,7 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_COMPUTE_WARPS = 8;
 constexpr int TC_THREADS = (TC_COMPUTE_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 16384;
-constexpr int TC_SLAB_COLS = 16;              // epilogue-3 transposition slab: 32 rows x 16 columns per warp
+constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 32 rows x 32 columns per warp
 constexpr int TC_SLAB_LD = TC_SLAB_COLS + 4;  // +4 floats: conflict-free float4 row writes / column reads
 
 template <int C1, int C2, int C3>
@@ -35,7 +35,7 @@ struct TcCfg {
     static constexpr int NCH3 = C3 / N3;
     static constexpr int A_BYTES = TC_ROWS * (C1 > C2 ? C1 : C2) * 4;
     static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
-    static constexpr int NSTAGE = (C1 >= 256) ? 4 : (C1 >= 128 ? 8 : JOBS);
+    static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 8 : JOBS);
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
     static constexpr int OFF_W = A_BYTES;
     static constexpr int OFF_RECS = OFF_W + NSTAGE * TC_STAGE_BYTES;
@@ -237,48 +237,39 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
             float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * TC_SLAB_LD);
-            const int scol = lane & 15, srow0 = (lane >> 4) * 16;
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
                 const uint32_t buf = chunk & 1;
                 mbar_wait(&acc3_full[buf], (chunk >> 1) & 1);
                 tc_fence_after();
-#pragma unroll
+#pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     const int col0 = h * 64 + half * 32;
                     uint32_t v[32];
                     tmem_ld32(lane_taddr + 256 + buf * 128 + col0, v);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int sub = 0; sub < 2; ++sub) {
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4)
-                            *(uint4 *)(slab + lane * TC_SLAB_LD + c4 * 4) =
-                                make_uint4(v[sub * 16 + c4 * 4], v[sub * 16 + c4 * 4 + 1],
-                                           v[sub * 16 + c4 * 4 + 2], v[sub * 16 + c4 * 4 + 3]);
-                        __syncwarp();
-                        const int c = nc * Cfg::N3 + col0 + sub * 16 + scol;
-                        const float bias = b3s[c];
-                        float run = -INFINITY;
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) {
-                            const int rr = srow0 + r;
-                            run = fmaxf(run, slab[rr * TC_SLAB_LD + scol]);
-                            if ((endmask >> rr) & 1u) {
-                                const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
-                                if (o > 0.f)
-                                    atomicMax(feat + (size_t)sect_s[q * 32 + rr] * p.ld_feat + c, __float_as_int(o));
-                                run = -INFINITY;
-                            }
-                        }
-                        // lanes 0-15 may hold the partial max of a section that continues into rows
-                        // 16..31 (no end bit at row 15): flush it as a partial — atomic max merges halves
-                        if (srow0 == 0 && !((endmask >> 15) & 1u) && (q * 32 + 15) < nrows) {
-                            const float o = to_tf32(run + bias);
-                            if (o > 0.f)
-                                atomicMax(feat + (size_t)sect_s[q * 32 + 15] * p.ld_feat + c, __float_as_int(o));
-                        }
-                        __syncwarp();
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *(uint4 *)(slab + lane * TC_SLAB_LD + c4 * 4) =
+                            make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                    __syncwarp();
+                    // lane = column; the warp walks its rows section by section (bounds are warp-uniform)
+                    const int c = nc * Cfg::N3 + col0 + lane;
+                    const float bias = b3s[c];
+                    const float *col = slab + lane;
+                    unsigned em = endmask;
+                    int start = 0;
+                    while (em) {
+                        const int end = __ffs(em) - 1;
+                        em &= em - 1;
+                        float run = col[start * TC_SLAB_LD];
+#pragma unroll 4
+                        for (int r = start + 1; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                        const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
+                        if (o > 0.f)
+                            atomicMax(feat + (size_t)sect_s[q * 32 + end] * p.ld_feat + c, __float_as_int(o));
+                        start = end + 1;
                     }
+                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();

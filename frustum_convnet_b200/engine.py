@@ -459,35 +459,51 @@ class _Plan:
         return o
 
     def time_kernels(self, dev_pool, iters=20):
-        """Per-kernel device time of the eager launch sequence, CUDA events on the launching stream,
-        averaged over `iters` forwards; plus executed/nominal FLOPs per launch (bench.py roofline)."""
+        """Per-kernel device time, measured live with CUDA events on the launching stream: each
+        C-ABI call is captured into its own one-node CUDA graph and replayed `iters` times back to
+        back between two events (hot L2, no host launch overhead, includes the inter-launch gap just
+        like the whole-forward graph does).  Also returns executed/nominal FLOPs per launch."""
         eng, S = self.eng, self.eng.arch.num_scales
         names = ["group_rows"] + ["pointnet_s%d" % (s + 1) for s in range(S)] + \
             [L.name for L in eng.layers] + ["decode_eval"]
+        d = dev_pool[0]
+        self.in_pc.copy_(d["point_cloud"])
+        for dst, i in zip(self.in_centers, range(S)):
+            dst.copy_(d["center_ref%d" % (i + 1)])
+        if eng.num_vec > 0:
+            self.in_onehot.copy_(d["one_hot"])
+        g = self.group_args
+        g.pc, g.one_hot = _ptr(self.in_pc), _ptr(self.in_onehot) if eng.num_vec > 0 else None
+        for s_, c in enumerate(self.in_centers):
+            g.centers[s_] = _ptr(c)
+
+        def call_group():
+            self.ntiles.zero_()
+            _lib.call("fcn_group_rows", C.byref(g), _stream())
+
+        calls = [call_group]
+        calls += [(lambda a=a: _lib.call("fcn_pointnet_tiles", C.byref(a), _stream())) for a in self.pn_args]
+        calls += [(lambda a=a: _lib.call("fcn_conv_gemm", C.byref(a), _stream())) for a in self.conv_args]
+        calls += [lambda: self._launch_decode(self.in_centers[1])]
         acc = np.zeros(len(names))
-        st = _stream()
         with torch.cuda.device(eng.device):
-            for it in range(iters + 2):
-                d = dev_pool[it % len(dev_pool)]
-                centers = [d["center_ref%d" % (i + 1)] for i in range(S)]
-                g = self.group_args
-                g.pc, g.one_hot = _ptr(d["point_cloud"]), _ptr(d["one_hot"]) if eng.num_vec > 0 else None
-                for s_, c in enumerate(centers):
-                    g.centers[s_] = _ptr(c)
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-                self.ntiles.zero_()
-                k = 0
-                ev[0].record()
-                _lib.call("fcn_group_rows", C.byref(g), st); k += 1; ev[k].record()
-                for a in self.pn_args:
-                    _lib.call("fcn_pointnet_tiles", C.byref(a), st); k += 1; ev[k].record()
-                for a in self.conv_args:
-                    _lib.call("fcn_conv_gemm", C.byref(a), st); k += 1; ev[k].record()
-                self._launch_decode(centers[1]); k += 1; ev[k].record()
+            for fn in calls:       # eager warm-up of the whole sequence (valid tiles/feats for later kernels)
+                fn()
+            torch.cuda.synchronize()
+            for i, fn in enumerate(calls):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    fn()
+                gr.replay()
                 torch.cuda.synchronize()
-                if it >= 2:
-                    acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
-        acc /= iters
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    gr.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                acc[i] = e0.elapsed_time(e1) / iters
+                del gr
         rows_exec = [int(c.sum().item()) for c in self.cnt]
         rows_nom = [self.B * self.T[s] * eng.arch.nsample[s] for s in range(S)]
         kern = [dict(name="group_rows", ms=float(acc[0]), executed_gflop=0.0, nominal_gflop=0.0)]
