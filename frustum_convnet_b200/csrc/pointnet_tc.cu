@@ -35,7 +35,7 @@ struct TcCfg {
     static constexpr int NCH3 = C3 / N3;
     static constexpr int A_BYTES = TC_ROWS * (C1 > C2 ? C1 : C2) * 4;
     static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
-    static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 8 : JOBS);
+    static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 6 : JOBS);
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
     static constexpr int OFF_W = A_BYTES;
     static constexpr int OFF_RECS = OFF_W + NSTAGE * TC_STAGE_BYTES;
@@ -50,6 +50,8 @@ struct TcCfg {
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
     static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 128 == 0, "channel counts");
     static_assert(C2 <= 256, "acc2 occupies TMEM columns [0,256)");
+    static_assert(C1 == C2, "a_ready phase bookkeeping assumes the same K-block count for A1 and A2");
+    static_assert(BYTES <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
 };
 
 template <int C1, int C2, int C3>
