@@ -460,8 +460,8 @@ class _Plan:
 
     def time_kernels(self, dev_pool, iters=20):
         """Per-kernel device time, measured live with CUDA events on the launching stream: each
-        C-ABI call is captured into its own one-node CUDA graph and replayed `iters` times back to
-        back between two events (hot L2, no host launch overhead, includes the inter-launch gap just
+        C-ABI call is captured `iters` times back to back into one CUDA graph, which is replayed
+        between two events (hot L2, no host launch overhead; includes the inter-kernel gap exactly
         like the whole-forward graph does).  Also returns executed/nominal FLOPs per launch."""
         eng, S = self.eng, self.eng.arch.num_scales
         names = ["group_rows"] + ["pointnet_s%d" % (s + 1) for s in range(S)] + \
@@ -492,17 +492,19 @@ class _Plan:
             torch.cuda.synchronize()
             for i, fn in enumerate(calls):
                 gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr):
-                    fn()
+                with torch.cuda.graph(gr):     # `iters` back-to-back launches of the same kernel in ONE graph
+                    for _ in range(iters):
+                        fn()
                 gr.replay()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 3
                 e0.record()
-                for _ in range(iters):
+                for _ in range(reps):
                     gr.replay()
                 e1.record()
                 torch.cuda.synchronize()
-                acc[i] = e0.elapsed_time(e1) / iters
+                acc[i] = e0.elapsed_time(e1) / (iters * reps)
                 del gr
         rows_exec = [int(c.sum().item()) for c in self.cnt]
         rows_nom = [self.B * self.T[s] * eng.arch.nsample[s] for s in range(S)]
