@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <utility>
 
 #include "../../include/frustum_b200.h"
 
@@ -40,5 +41,31 @@ inline int cuda_fail(const char *fn, cudaError_t e) {
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 int sm_count();
+
+// Programmatic dependent launch (PDL): every kernel of the forward chain is launched with the
+// programmatic-stream-serialization attribute, executes `griddepcontrol.wait` before its first
+// global-memory access (full completion + memory flush of the previous grid) and releases its own
+// dependents right after, so launch latency / CTA rasterisation / barrier+TMEM prologues of kernel
+// N+1 overlap the tail of kernel N.  Works unchanged under CUDA-graph capture.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 }  // namespace fcn

@@ -28,6 +28,8 @@ conv_gemm_simt_kernel(const __grid_constant__ fcn_conv_args p) {
     const int M = p.B * p.T_out;
     const int m0 = blockIdx.x * CG_TM, n0 = blockIdx.y * CG_TN;
     const int nchunks = p.K_pad / CG_KC;
+    pdl_wait();
+    pdl_launch_dependents();
 
     // loader coordinates: A: rows (tid>>3) and +32, 4 channels at (tid&7)*4;  W: rows (tid>>4), +16
     const int arow = tid >> 3, acol = (tid & 7) * 4;
@@ -131,8 +133,7 @@ int conv_gemm_simt(const fcn_conv_args &a, cudaStream_t stream) {
     const int M = a.B * a.T_out;
     if (M == 0) return FCN_OK;
     dim3 grid(ceil_div(M, CG_TM), a.n_cols / CG_TN);
-    conv_gemm_simt_kernel<<<grid, CG_THREADS, 0, stream>>>(a);
-    FCN_LAUNCH_CHECK();
+    FCN_CUDA(launch_pdl(conv_gemm_simt_kernel, grid, dim3(CG_THREADS), (size_t)0, stream, a));
     return FCN_OK;
 }
 

@@ -60,6 +60,8 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // prologue above overlapped the previous layer's tail
+    pdl_launch_dependents();
 
     if (warp == GT_PROD_WARPS + 1) {
         // ================= weight loader =================
@@ -180,8 +182,7 @@ static int launch_gt(const fcn_conv_args &a, cudaStream_t stream) {
     FCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
     const int M = a.B * a.T_out;
     dim3 grid(ceil_div(M, GT_ROWS), a.n_cols / NT);
-    kern<<<grid, GT_THREADS, Cfg::BYTES, stream>>>(a);
-    FCN_LAUNCH_CHECK();
+    FCN_CUDA(launch_pdl(kern, grid, dim3(GT_THREADS), (size_t)Cfg::BYTES, stream, a));
     return FCN_OK;
 }
 

@@ -17,6 +17,8 @@ __global__ void decode_eval_kernel(int B, int T, int ld, int NH, int NS,
                                    float *__restrict__ size, float *__restrict__ heading_probs,
                                    float *__restrict__ size_probs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
     if (r >= B * T) return;
     const int b = r / T, t = r - b * T;
     const float *row = logits + (size_t)r * ld;
@@ -127,10 +129,9 @@ extern "C" int fcn_decode_eval(int B, int T, int ld, int num_heading_bin, int nu
     FCN_REQUIRE(logits && center_ref && mean_size && cls_probs && center && heading && size &&
                     heading_probs && size_probs, "NULL pointer");
     const int n = B * T;
-    decode_eval_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(
-        B, T, ld, num_heading_bin, num_size, logits, center_ref, mean_size, cls_probs, center,
-        heading, size, heading_probs, size_probs);
-    FCN_LAUNCH_CHECK();
+    FCN_CUDA(launch_pdl(decode_eval_kernel, dim3(ceil_div(n, 128)), dim3(128), (size_t)0, (cudaStream_t)stream,
+                        B, T, ld, num_heading_bin, num_size, logits, center_ref, mean_size, cls_probs,
+                        center, heading, size, heading_probs, size_probs));
     return FCN_OK;
 }
 

@@ -93,6 +93,10 @@ group_count_kernel(const __grid_constant__ GroupParams P) {
     extern __shared__ float sz[];        // z row of this frustum
     const fcn_group_args &a = P.a;
     const int b = blockIdx.y;
+    pdl_wait();
+    pdl_launch_dependents();
+    // the tile counters of this forward are reset here (group_emit_kernel runs after this grid)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < FCN_MAX_SCALES) a.ntiles[threadIdx.x] = 0;
     // blockIdx.x enumerates (scale, 32-section chunk) pairs
     int s = 0, chunk = blockIdx.x;
     for (; s < a.num_scales; ++s) {
@@ -142,7 +146,9 @@ group_emit_kernel(const __grid_constant__ GroupParams P) {
     float *scen = (float *)(sm_i + 2 * T);     // 3T: section centres (x | y | z)
     __shared__ int s_warp_tot[GE_THREADS / 32];
     __shared__ int s_carry, s_total, s_tile_base;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_launch_dependents();
     const int *gcnt = a.cnt[s] + (size_t)b * T;
     for (int i = threadIdx.x; i < T; i += blockDim.x) scnt[i] = gcnt[i];
     {
@@ -300,10 +306,8 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
     int nchunks = 0;
     for (int s = 0; s < a.num_scales; ++s) nchunks += ceil_div(a.T[s], GC_WARPS);
     dim3 gc(nchunks, a.B);
-    group_count_kernel<<<gc, GC_WARPS * 32, smem_c, (cudaStream_t)stream>>>(P);
-    FCN_LAUNCH_CHECK();
+    FCN_CUDA(launch_pdl(group_count_kernel, gc, dim3(GC_WARPS * 32), smem_c, (cudaStream_t)stream, P));
     dim3 ge(a.B, a.num_scales);
-    group_emit_kernel<<<ge, GE_THREADS, smem_e, (cudaStream_t)stream>>>(P);
-    FCN_LAUNCH_CHECK();
+    FCN_CUDA(launch_pdl(group_emit_kernel, ge, dim3(GE_THREADS), smem_e, (cudaStream_t)stream, P));
     return FCN_OK;
 }

@@ -108,6 +108,8 @@ pointnet_simt_kernel(const __grid_constant__ fcn_pointnet_args p) {
     __shared__ int s_nrank, s_w0;
 
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    pdl_wait();
+    pdl_launch_dependents();
     const int ntiles = min(*p.ntiles, p.max_tiles);
     const int4 *tiles = (const int4 *)p.tiles;
 
@@ -234,8 +236,7 @@ static int launch_simt(const fcn_pointnet_args &a, cudaStream_t stream) {
     int grid = sm_count() * occ;
     if (grid > a.max_tiles) grid = a.max_tiles;
     if (grid < 1) return FCN_OK;
-    kern<<<grid, PT_THREADS, S::bytes, stream>>>(a);
-    FCN_LAUNCH_CHECK();
+    FCN_CUDA(launch_pdl(kern, dim3(grid), dim3(PT_THREADS), (size_t)S::bytes, stream, a));
     return FCN_OK;
 }
 

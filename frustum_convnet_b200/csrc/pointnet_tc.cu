@@ -75,6 +75,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_wait();                 // tile table / rows / feature map come from the grouping kernels
+    pdl_launch_dependents();
     const int ntiles = min(*p.ntiles, p.max_tiles);
     if ((int)blockIdx.x >= ntiles) return;  // whole CTA exits together: nothing was started
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -295,8 +297,7 @@ static int launch_tc(const fcn_pointnet_args &a, cudaStream_t stream) {
     int grid = sm_count();
     if (grid > a.max_tiles) grid = a.max_tiles;
     if (grid < 1) return FCN_OK;
-    kern<<<grid, TC_THREADS, Cfg::BYTES, stream>>>(a);
-    FCN_LAUNCH_CHECK();
+    FCN_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), (size_t)Cfg::BYTES, stream, a));
     return FCN_OK;
 }
 

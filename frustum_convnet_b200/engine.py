@@ -354,7 +354,6 @@ class _Plan:
         for s, c in enumerate(centers):
             g.centers[s] = _ptr(c)
         st = _stream()
-        self.ntiles.zero_()
         _lib.call("fcn_group_rows", C.byref(g), st)
         for a in self.pn_args:
             _lib.call("fcn_pointnet_tiles", C.byref(a), st)
@@ -478,7 +477,6 @@ class _Plan:
             g.centers[s_] = _ptr(c)
 
         def call_group():
-            self.ntiles.zero_()
             _lib.call("fcn_group_rows", C.byref(g), _stream())
 
         calls = [call_group]

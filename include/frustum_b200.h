@@ -72,7 +72,7 @@ FCN_API int fcn_query_depth_point_b3n(int b, int n, int m, float dis_z, int nsam
  *     Side outputs: cnt[s] (B,T_s) int32; feat[s] (B,T_s,ld_feat[s]) fp32 position-major is
  *     zero-filled and its one-hot channels [c3[s], c3[s]+num_vec) are written (det_base.py:145-157).
  *     idx_scratch[s] receives the selected point indices (the valid prefix of the reference idx).
- *     `ntiles` (int32[FCN_MAX_SCALES]) must be zero before the call (cudaMemsetAsync by caller).
+ *     `ntiles` (int32[FCN_MAX_SCALES]) is reset by the call itself.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     int num_scales, B, N, num_vec, tile_rows, unique_rows;
