@@ -62,6 +62,7 @@ class ConvArgs(C.Structure):
         ("wt", C.c_void_p), ("bias", C.c_void_p), ("w_tc", C.c_void_p),
         ("out", C.c_void_p),
         ("ld_out", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int), ("round_out", C.c_int),
+        ("dbg_clocks", C.c_void_p),
     ]
 
 

@@ -79,10 +79,15 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(128, NT);
             const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
+            const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
             for (int kb = 0; kb < KB; ++kb) {
                 const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
+                long long t0 = 0, t1 = 0, t2 = 0;
+                if (dbg) t0 = clock64();
                 mbar_wait(&a_full[st], ph);
+                if (dbg) t1 = clock64();
                 mbar_wait(&w_full[st], ph);
+                if (dbg) t2 = clock64();
                 fence_proxy_async();   // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
                 tc_fence_after();
 #pragma unroll
@@ -90,6 +95,10 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
                     mma_tf32(tmem_base, make_desc_sw128(sA_addr + st * Cfg::A_STAGE + k * 32),
                              make_desc_sw128(sW_addr + st * Cfg::W_STAGE + k * 32), idesc, (kb | k) != 0);
                 mma_commit(&empty[st]);
+                if (dbg) {
+                    long long *d = p.dbg_clocks + (size_t)kb * 8;
+                    d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64();
+                }
             }
             mma_commit(acc_full);
         }
@@ -123,7 +132,11 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
             const fcn_conv_seg sg = p.seg[seg];
             const int ch = seg_c0 + chunk * 4;
             const bool ch_ok = ch < sg.ld;                     // ld is a multiple of 4; pad columns are zero
+            const bool dbgp = p.dbg_clocks != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+            long long tp0 = 0;
+            if (dbgp) tp0 = clock64();
             mbar_wait(&empty[st], ph ^ 1);
+            if (dbgp) { p.dbg_clocks[(size_t)kb * 8 + 4] = tp0; p.dbg_clocks[(size_t)kb * 8 + 5] = clock64(); }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int ts = gt[j] * sg.stride + sg.tap;
@@ -136,6 +149,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&a_full[st]))
                          : "memory");
+            if (dbgp) p.dbg_clocks[(size_t)kb * 8 + 6] = clock64();
             seg_c0 += 32;
             if (seg_c0 >= ((sg.C + 31) / 32) * 32) { seg_c0 = 0; ++seg; if (seg >= p.n_seg) seg = p.n_seg - 1; }
         }

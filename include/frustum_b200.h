@@ -139,6 +139,7 @@ typedef struct {
     float *out;
     int ld_out, T_store, c_off;
     int round_out;   /* 1: round outputs to TF32 (cvt.rna) because a tensor-core GEMM consumes them */
+    long long *dbg_clocks; /* optional (NULL): CTA (0,0) dumps per-K-block pipeline timestamps, 8 per K block */
 } fcn_conv_args;
 FCN_API int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream);
 
