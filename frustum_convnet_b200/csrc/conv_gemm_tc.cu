@@ -1,11 +1,17 @@
 // 1-D conv / transposed conv / 1x1 conv (+ folded BN, optional ReLU) as an implicit GEMM on the
-// 5th-gen tensor cores ("precision = 1"): tcgen05.mma kind::tf32, accumulator in TMEM, weights
-// staged by the TMA engine (bulk copies of pre-swizzled [N_TILE x 32] stage images), activations
-// gathered from the position-major maps (taps / concat segments / zero padding) with 16-byte
-// cp.async (LDGSTS, zero-fill) issued by one thread per output row straight into the K-major
-// 128B-swizzled operand layout — no register staging, NSTAGE K blocks in flight.  Activations in
-// HBM are already TF32-rounded by their producers (cvt.rna in the epilogues, `round_out`), so the
-// tensor core's operand truncation is exact.
+// 5th-gen tensor cores ("precision = 1|2"): tcgen05.mma kind::tf32, accumulator in TMEM, weights
+// staged by the TMA engine (bulk copies of pre-swizzled [N_TILE x 32] images), activations gathered
+// from the position-major maps (taps / concat segments / zero padding) with coalesced 16-byte
+// cp.async (LDGSTS, zero-fill) straight into the K-major 128B-swizzled operand layout.
+// Activations in HBM are already TF32-rounded by their producers (`round_out`), so the tensor
+// core's operand truncation is exact.
+//
+// Pipeline (measured design points): one stage = 64 K elements (two 128-byte swizzle
+// atoms) so that the single-thread costs — one mbarrier wait (~170 clk even when already complete),
+// one proxy fence, one commit — are paid once per 8 MMAs; A and W of a stage complete on ONE mbarrier
+// (128 cp.async arrivals + the bulk copy's transaction bytes); the MMA warp runs warp-uniform and
+// issues through an elected lane; producers keep per-segment row pointers in registers so a K block
+// costs ~16 instructions per thread.
 // Same math as conv_gemm_simt.cu; replaces the Conv1d/DeConv1d/cat/head calls of
 // /root/reference/models/det_base.py:196-224,367-368.
 #include "common.cuh"
@@ -15,41 +21,48 @@ namespace fcn {
 using namespace umma;
 
 constexpr int GT_ROWS = 128;
-constexpr int GT_PROD_WARPS = 4;                 // thread = output row (A producer, then epilogue)
+constexpr int GT_PROD_WARPS = 4;                 // A producers, then epilogue (thread = output row)
 constexpr int GT_THREADS = (GT_PROD_WARPS + 2) * 32;
-constexpr int GT_NSTAGE = 6;
 
 template <int NT>
 struct GtCfg {
-    static constexpr int A_STAGE = GT_ROWS * 128, W_STAGE = NT * 128;
-    static constexpr int OFF_W = GT_NSTAGE * A_STAGE;
-    static constexpr int OFF_BAR = OFF_W + GT_NSTAGE * W_STAGE;
-    static constexpr int NBAR = 3 * GT_NSTAGE + 1;
+    static constexpr int NSTAGE = NT > 64 ? 3 : 4;
+    static constexpr int A_ATOM = GT_ROWS * 128, W_ATOM = NT * 128;
+    static constexpr int A_STAGE = 2 * A_ATOM, W_STAGE = 2 * W_ATOM;
+    static constexpr int OFF_W = NSTAGE * A_STAGE;
+    static constexpr int OFF_BAR = OFF_W + NSTAGE * W_STAGE;
+    static constexpr int NBAR = 2 * NSTAGE + 1;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;
+    static_assert(BYTES <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
 };
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 
 template <int NT>
 __global__ void __launch_bounds__(GT_THREADS)
 conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
     using Cfg = GtCfg<NT>;
+    constexpr int NSTAGE = Cfg::NSTAGE;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     uint8_t *sA = smem, *sW = smem + Cfg::OFF_W;
     uint64_t *bars = (uint64_t *)(smem + Cfg::OFF_BAR);
-    uint64_t *a_full = bars, *w_full = bars + GT_NSTAGE, *empty = bars + 2 * GT_NSTAGE;
-    uint64_t *acc_full = bars + 3 * GT_NSTAGE;
+    uint64_t *full = bars, *empty = bars + NSTAGE, *acc_full = bars + 2 * NSTAGE;
     uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = p.B * p.T_out;
     const int m0 = blockIdx.x * GT_ROWS, n_tile = blockIdx.y;
-    const int KB = p.K_pad / 32;
+    const int NS = p.K_pad / 64;                 // pipeline stages of 64 K elements
 
     if (tid == 0) {
-        for (int i = 0; i < GT_NSTAGE; ++i) {
-            mbar_init(&a_full[i], GT_PROD_WARPS * 32);
-            mbar_init(&w_full[i], 1);
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&full[i], GT_PROD_WARPS * 32 + 1);   // 128 cp.async arrivals + the W loader
             mbar_init(&empty[i], 1);
         }
         mbar_init(acc_full, 1);
@@ -64,52 +77,51 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
     pdl_launch_dependents();
 
     if (warp == GT_PROD_WARPS + 1) {
-        // ================= weight loader =================
+        // ================= weight loader (one lane) =================
         if (lane == 0) {
-            const uint8_t *src = (const uint8_t *)p.w_tc + (size_t)n_tile * KB * Cfg::W_STAGE;
-            for (int kb = 0; kb < KB; ++kb) {
-                const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
+            const uint8_t *src = (const uint8_t *)p.w_tc + (size_t)n_tile * NS * Cfg::W_STAGE;
+            for (int s = 0; s < NS; ++s) {
+                const int st = s % NSTAGE, ph = (s / NSTAGE) & 1;
                 mbar_wait(&empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&w_full[st], Cfg::W_STAGE);
-                bulk_g2s(sW + st * Cfg::W_STAGE, src + (size_t)kb * Cfg::W_STAGE, Cfg::W_STAGE, &w_full[st]);
+                mbar_arrive_expect_tx(&full[st], Cfg::W_STAGE);
+                bulk_g2s(sW + st * Cfg::W_STAGE, src + (size_t)s * Cfg::W_STAGE, Cfg::W_STAGE, &full[st]);
             }
         }
     } else if (warp == GT_PROD_WARPS) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(128, NT);
-            const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
-            const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-            for (int kb = 0; kb < KB; ++kb) {
-                const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
-                long long t0 = 0, t1 = 0, t2 = 0;
-                if (dbg) t0 = clock64();
-                mbar_wait(&a_full[st], ph);
-                if (dbg) t1 = clock64();
-                mbar_wait(&w_full[st], ph);
-                if (dbg) t2 = clock64();
+        // ================= MMA issuer: warp-uniform control flow, elected lane issues =================
+        constexpr uint32_t idesc = make_idesc_tf32(128, NT);
+        const uint64_t adesc0 = make_desc_sw128(smem_u32(sA));
+        const uint64_t bdesc0 = make_desc_sw128(smem_u32(sW));
+        const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+        for (int s = 0; s < NS; ++s) {
+            const int st = s % NSTAGE, ph = (s / NSTAGE) & 1;
+            long long t0 = 0, t1 = 0;
+            if (dbg) t0 = clock64();
+            mbar_wait(&full[st], ph);
+            if (dbg) t1 = clock64();
+            tc_fence_after();
+            if (elect_one()) {
                 fence_proxy_async();   // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
-                tc_fence_after();
+                const uint64_t ad = adesc0 + (uint64_t)(st * (Cfg::A_STAGE >> 4));
+                const uint64_t bd = bdesc0 + (uint64_t)(st * (Cfg::W_STAGE >> 4));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_tf32(tmem_base, make_desc_sw128(sA_addr + st * Cfg::A_STAGE + k * 32),
-                             make_desc_sw128(sW_addr + st * Cfg::W_STAGE + k * 32), idesc, (kb | k) != 0);
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_tf32(tmem_base, ad + (uint64_t)(a * (Cfg::A_ATOM >> 4) + 2 * k),
+                                 bd + (uint64_t)(a * (Cfg::W_ATOM >> 4) + 2 * k), idesc, (s | a | k) != 0);
                 mma_commit(&empty[st]);
-                if (dbg) {
-                    long long *d = p.dbg_clocks + (size_t)kb * 8;
-                    d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64();
-                }
             }
-            mma_commit(acc_full);
+            __syncwarp();
+            if (dbg) {
+                long long *d = p.dbg_clocks + (size_t)s * 8;
+                d[0] = t0; d[1] = t1; d[2] = t1; d[3] = clock64();
+            }
         }
+        if (elect_one()) mma_commit(acc_full);
+        __syncwarp();
     } else {
-        // ================= A producers (thread = row), then epilogue =================
-        const int row = warp * 32 + lane;
-        const int r = m0 + row;
-        const bool row_ok = r < M;
-        const int rb = row_ok ? r / p.T_out : 0;
-        const int rt = row_ok ? r - rb * p.T_out : 0;
-
+        // ================= A producers, then epilogue =================
         // Coalesced gather: one warp instruction covers 4 rows x 128 B (lane -> row j*4 + lane/8,
         // 16-byte chunk lane%8), i.e. 4 full cache lines instead of 32 partial ones.
         const int chunk = lane & 7;
@@ -126,34 +138,58 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
             gok |= (okr ? 1u : 0u) << j;
             gdst[j] = smem_u32(sA) + (uint32_t)((lr >> 3) * 1024 + (lr & 7) * 128 + ((chunk ^ (lr & 7)) << 4));
         }
-        int seg = 0, seg_c0 = 0;   // running (segment, channel offset) of the current K block
-        for (int kb = 0; kb < KB; ++kb) {
-            const int st = kb % GT_NSTAGE, ph = (kb / GT_NSTAGE) & 1;
+        const bool dbgp = p.dbg_clocks != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+        int kbg = 0;                    // global 32-wide K-block index
+        for (int seg = 0; seg < p.n_seg; ++seg) {
             const fcn_conv_seg sg = p.seg[seg];
-            const int ch = seg_c0 + chunk * 4;
-            const bool ch_ok = ch < sg.ld;                     // ld is a multiple of 4; pad columns are zero
-            const bool dbgp = p.dbg_clocks != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
-            long long tp0 = 0;
-            if (dbgp) tp0 = clock64();
-            mbar_wait(&empty[st], ph ^ 1);
-            if (dbgp) { p.dbg_clocks[(size_t)kb * 8 + 4] = tp0; p.dbg_clocks[(size_t)kb * 8 + 5] = clock64(); }
+            const float *rp[8];         // channel-0 address of the 8 source rows for this segment
+            unsigned okm = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int ts = gt[j] * sg.stride + sg.tap;
-                const bool ok = ch_ok && ((gok >> j) & 1u) && ts >= 0 && ts < sg.T_src;
-                const float *src = ok ? sg.src + ((size_t)gb[j] * sg.T_src + ts) * sg.ld + ch : sg.src;
-                const int sz = ok ? 16 : 0;                    // src-size 0 -> 16 bytes of zeros
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(gdst[j] + st * Cfg::A_STAGE),
-                             "l"(src), "r"(sz)
-                             : "memory");
+                const bool ok = ((gok >> j) & 1u) && ts >= 0 && ts < sg.T_src;
+                okm |= (ok ? 1u : 0u) << j;
+                rp[j] = sg.src + ((size_t)gb[j] * sg.T_src + (ok ? ts : 0)) * sg.ld + chunk * 4;
             }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&a_full[st]))
-                         : "memory");
-            if (dbgp) p.dbg_clocks[(size_t)kb * 8 + 6] = clock64();
-            seg_c0 += 32;
-            if (seg_c0 >= ((sg.C + 31) / 32) * 32) { seg_c0 = 0; ++seg; if (seg >= p.n_seg) seg = p.n_seg - 1; }
+            const int nkb = (sg.C + 31) >> 5;
+            for (int kbi = 0; kbi < nkb; ++kbi, ++kbg) {
+                const int s = kbg >> 1, st = s % NSTAGE, ph = (s / NSTAGE) & 1;
+                if ((kbg & 1) == 0) {
+                    long long tp0 = 0;
+                    if (dbgp) tp0 = clock64();
+                    mbar_wait(&empty[st], ph ^ 1);
+                    if (dbgp) { p.dbg_clocks[(size_t)s * 8 + 4] = tp0; p.dbg_clocks[(size_t)s * 8 + 5] = clock64(); }
+                }
+                const unsigned m = (kbi * 32 + chunk * 4 < sg.ld) ? okm : 0u;   // pad columns / past ld: zeros
+                const uint32_t dofs = st * Cfg::A_STAGE + (kbg & 1) * Cfg::A_ATOM;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(gdst[j] + dofs),
+                                 "l"(rp[j] + kbi * 32), "r"(((m >> j) & 1u) ? 16 : 0)
+                                 : "memory");
+                if (kbg & 1) {
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full[st]))
+                                 : "memory");
+                    if (dbgp) p.dbg_clocks[(size_t)s * 8 + 6] = clock64();
+                }
+            }
         }
-        // ---- epilogue: TMEM -> +bias (+ReLU) -> position-major global store
+        if (kbg & 1) {   // odd number of K blocks: the second atom of the last stage is all zeros
+            const int s = kbg >> 1, st = s % NSTAGE;
+            const uint32_t dofs = st * Cfg::A_STAGE + Cfg::A_ATOM;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(gdst[j] + dofs), "l"(p.wt), "r"(0)
+                             : "memory");
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full[st]))
+                         : "memory");
+        }
+        // ---- epilogue: TMEM -> +bias (+ReLU, TF32 rounding) -> position-major global store
+        const int row = warp * 32 + lane;
+        const int r = m0 + row;
+        const bool row_ok = r < M;
+        const int rb = row_ok ? r / p.T_out : 0;
+        const int rt = row_ok ? r - rb * p.T_out : 0;
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -204,6 +240,7 @@ static int launch_gt(const fcn_conv_args &a, cudaStream_t stream) {
 int conv_gemm_tc(const fcn_conv_args &a, cudaStream_t stream) {
     FCN_REQUIRE(a.w_tc != nullptr, "NULL tensor-core weight image");
     FCN_REQUIRE(a.Cout % 32 == 0, "tensor-core variant needs Cout % 32 == 0");
+    FCN_REQUIRE(a.K_pad % 64 == 0, "tensor-core variant needs K_pad % 64 == 0");
     if (a.B * a.T_out == 0) return FCN_OK;
     if (a.precision == 2) return launch_gt<64>(a, stream);
     FCN_REQUIRE(a.n_cols % 128 == 0, "n_cols must be a multiple of 128 for the 128-wide N tile");

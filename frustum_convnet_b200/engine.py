@@ -69,6 +69,9 @@ class _ConvLayer:
         self.name, self.segs, self.K_pad, self.n_cols = name, segs, K_pad, n_cols
         self.Cout, self.up, self.relu, self.wt, self.bias = Cout, up, relu, wt, bias
         self.out, self.c_off = out, c_off
+        if K_pad % 64:   # tensor-core stages are 64 K elements wide: one extra all-zero K block
+            self.wt = torch.cat([wt, torch.zeros(32, wt.shape[1], dtype=wt.dtype, device=wt.device)], 0).contiguous()
+            self.K_pad = K_pad + 32
         self._tc = {}
 
     def tc_image(self, n_tile: int) -> torch.Tensor:

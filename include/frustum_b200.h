@@ -123,7 +123,8 @@ FCN_API int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t strea
  *     (models/det_base.py:167-224, factories models/common.py:38-63), the torch.cat calls
  *     (multi-segment A operand) and the two heads (det_base.py:367-368).
  *       out[b, t*up + j, c_off + co] = act( sum_seg sum_c src[b, t*stride + tap, c] * W + bias )
- *     K is the concatenation of the segments, each padded to a multiple of 32 (zero weights).
+ *     K is the concatenation of the segments, each padded to a multiple of 32 (zero weights); K_pad
+ *     is that sum, optionally rounded up to a multiple of 64 (required by the tensor-core variants).
  *     wt: [K_pad][n_cols] fp32 (n_cols = up*Cout rounded up to 64), bias: [n_cols].
  * ------------------------------------------------------------------------------------------ */
 typedef struct {

@@ -22,7 +22,7 @@ eng = m.engine()
 plan = eng.plan(32, 1024, [280, 140, 70, 35])
 idx = [L.name for L in eng.layers].index(layer)
 a = plan.conv_args[idx]
-KB = a.K_pad // 32
+KB = a.K_pad // 64
 buf = torch.zeros(KB * 8, dtype=torch.int64, device="cuda")
 a.dbg_clocks = buf.data_ptr()
 st = torch.cuda.current_stream().cuda_stream
