@@ -37,7 +37,7 @@ struct GtCfg {
     static_assert(BYTES <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
 };
 
-__device__ __forceinline__ bool elect_one() {
+__device__ __forceinline__ bool gt_elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
     return pred != 0;
@@ -100,7 +100,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
             mbar_wait(&full[st], ph);
             if (dbg) t1 = clock64();
             tc_fence_after();
-            if (elect_one()) {
+            if (gt_elect_one()) {
                 fence_proxy_async();   // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
                 const uint64_t ad = adesc0 + (uint64_t)(st * (Cfg::A_STAGE >> 4));
                 const uint64_t bd = bdesc0 + (uint64_t)(st * (Cfg::W_STAGE >> 4));
@@ -118,7 +118,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
                 d[0] = t0; d[1] = t1; d[2] = t1; d[3] = clock64();
             }
         }
-        if (elect_one()) mma_commit(acc_full);
+        if (gt_elect_one()) mma_commit(acc_full);
         __syncwarp();
     } else {
         // ================= A producers, then epilogue =================

@@ -25,6 +25,12 @@ constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 32 rows x 32 columns per warp
 constexpr int TC_SLAB_LD = TC_SLAB_COLS + 4;  // +4 floats: conflict-free float4 row writes / column reads
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int C1, int C2, int C3>
 struct TcCfg {
     static constexpr int KB1 = C1 / 32, KB2 = C2 / 32;
@@ -120,48 +126,55 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             }
         }
     } else if (warp == TC_COMPUTE_WARPS) {
-        // ================= MMA issuer (one elected lane) =================
-        if (lane == 0) {
-            constexpr uint32_t idesc2 = make_idesc_tf32(128, Cfg::N2);
-            constexpr uint32_t idesc3 = make_idesc_tf32(128, Cfg::N3);
-            uint32_t job = 0, chunk = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                if (Cfg::RESIDENT) job = 0;
-                // ---- layer 2
-                for (int nc = 0; nc < Cfg::NCH2; ++nc) {
-                    for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
-                        const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
-                        if (nc == 0) mbar_wait(&a_ready[kb], 0);
-                        mbar_wait(&w_full[st], ph);
-                        tc_fence_after();
-                        const uint32_t a0 = sA_addr + kb * (TC_ROWS * 128), b0 = sW_addr + st * TC_STAGE_BYTES;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_tf32(tmem_base + nc * Cfg::N2, make_desc_sw128(a0 + k * 32),
-                                     make_desc_sw128(b0 + k * 32), idesc2, (kb | k) != 0);
-                        if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
-                    }
-                }
-                mma_commit(acc2_full);
-                // ---- layer 3
-                for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
-                    const uint32_t buf = chunk & 1;
-                    mbar_wait(&acc3_empty[buf], ((chunk >> 1) & 1) ^ 1);
+        // ================= MMA issuer: warp-uniform control flow, elected lane issues =================
+        constexpr uint32_t idesc2 = make_idesc_tf32(128, Cfg::N2);
+        constexpr uint32_t idesc3 = make_idesc_tf32(128, Cfg::N3);
+        const uint64_t adesc0 = make_desc_sw128(sA_addr), bdesc0 = make_desc_sw128(sW_addr);
+        uint32_t job = 0, chunk = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            if (Cfg::RESIDENT) job = 0;
+            // ---- layer 2
+            for (int nc = 0; nc < Cfg::NCH2; ++nc) {
+                for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
+                    const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
+                    if (nc == 0) mbar_wait(&a_ready[kb], 0);
+                    mbar_wait(&w_full[st], ph);
                     tc_fence_after();
-                    for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
-                        const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
-                        if (nc == 0) mbar_wait(&a_ready[kb], 1);
-                        mbar_wait(&w_full[st], ph);
-                        tc_fence_after();
-                        const uint32_t a0 = sA_addr + kb * (TC_ROWS * 128), b0 = sW_addr + st * TC_STAGE_BYTES;
+                    if (elect_one()) {
+                        const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
+                        const uint64_t bd = bdesc0 + (uint64_t)(st * (TC_STAGE_BYTES >> 4));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_tf32(tmem_base + 256 + buf * 128, make_desc_sw128(a0 + k * 32),
-                                     make_desc_sw128(b0 + k * 32), idesc3, (kb | k) != 0);
+                            mma_tf32(tmem_base + nc * Cfg::N2, ad + 2 * k, bd + 2 * k, idesc2, (kb | k) != 0);
                         if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
                     }
-                    mma_commit(&acc3_full[buf]);
+                    __syncwarp();
                 }
+            }
+            if (elect_one()) mma_commit(acc2_full);
+            __syncwarp();
+            // ---- layer 3
+            for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
+                const uint32_t buf = chunk & 1;
+                mbar_wait(&acc3_empty[buf], ((chunk >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
+                    const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
+                    if (nc == 0) mbar_wait(&a_ready[kb], 1);
+                    mbar_wait(&w_full[st], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
+                        const uint64_t bd = bdesc0 + (uint64_t)(st * (TC_STAGE_BYTES >> 4));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_tf32(tmem_base + 256 + buf * 128, ad + 2 * k, bd + 2 * k, idesc3, (kb | k) != 0);
+                        if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) mma_commit(&acc3_full[buf]);
+                __syncwarp();
             }
         }
     } else {

@@ -287,6 +287,7 @@ class _Plan:
         self.in_centers = [torch.empty((B, 3, T[s]), dtype=f32, device=dev) for s in range(S)]
         self.in_onehot = torch.zeros((B, max(eng.num_vec, 1)), dtype=f32, device=dev)
         self.graph = None
+        self._sides = []
         self._build_args()
 
     def _tsize(self, name):
@@ -339,9 +340,9 @@ class _Plan:
             a.K_pad, a.n_cols, a.Cout, a.up, a.relu = L.K_pad, L.n_cols, L.Cout, L.up, L.relu
             a.precision, a.w_tc = 0, None
             if eng.precision == 1 and L.Cout % 32 == 0:
-                # N tile 128 when that already gives enough CTAs, else 64 (more, smaller tiles)
-                m_tiles = (a.B * a.T_out + 127) // 128
-                nt = 128 if (L.n_cols % 128 == 0 and m_tiles * (L.n_cols // 128) >= 96) else 64
+                # The A operand (LDGSTS gather, ~37 B/clk/SM measured) is the feed limit, so the wider
+                # N tile (2x the MMA work per gathered A byte) wins whenever the layer has >= 128 columns.
+                nt = 128 if L.n_cols % 128 == 0 else 64
                 a.precision = 1 if nt == 128 else 2
                 a.w_tc = _ptr(L.tc_image(nt))
             a.round_out = 1 if (eng.precision == 1 and L.name != "heads") else 0
@@ -356,15 +357,66 @@ class _Plan:
         g.one_hot = _ptr(one_hot) if self.eng.num_vec > 0 else None
         for s, c in enumerate(centers):
             g.centers[s] = _ptr(c)
-        st = _stream()
-        _lib.call("fcn_group_rows", C.byref(g), st)
-        for a in self.pn_args:
-            _lib.call("fcn_pointnet_tiles", C.byref(a), st)
+        main = torch.cuda.current_stream()
+        _lib.call("fcn_group_rows", C.byref(g), main.cuda_stream)
+        # the S scales are independent: fork them onto side streams (largest first, on the main stream)
+        # so that the tile tail of one scale is filled by CTAs of the next (also inside the CUDA graph)
+        S = len(self.pn_args)
+        if S == 0:
+            return
+        side = self._side_streams(S - 1)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        order = list(range(S - 1, -1, -1))
+        joins = []
+        for rank, s_ in enumerate(order):
+            if rank == 0:
+                _lib.call("fcn_pointnet_tiles", C.byref(self.pn_args[s_]), main.cuda_stream)
+            else:
+                st = side[rank - 1]
+                st.wait_event(fork)
+                _lib.call("fcn_pointnet_tiles", C.byref(self.pn_args[s_]), st.cuda_stream)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
+
+    def _side_streams(self, n):
+        while len(self._sides) < n:
+            self._sides.append(torch.cuda.Stream(device=self.eng.device))
+        return self._sides
 
     def _launch_fcn(self):
-        st = _stream()
-        for a in self.conv_args:
-            _lib.call("fcn_conv_gemm", C.byref(a), st)
+        """Main chain on the current stream; the transposed convs of all but the last block only
+        feed the final concat, so they run on a side stream next to the following block."""
+        main = torch.cuda.current_stream()
+        names = [L.name for L in self.eng.layers]
+        deconvs = [n for n in names if n.endswith("_deconv")]
+        side_set = set(deconvs[:-1])
+        side = self._side_streams(1)[0] if side_set else None
+        joins = []
+        for a, L in zip(self.conv_args, self.eng.layers):
+            if L.name in side_set:
+                continue
+            if L.name == "heads":
+                for ev in joins:
+                    main.wait_event(ev)
+            _lib.call("fcn_conv_gemm", C.byref(a), main.cuda_stream)
+            if L.name.endswith("_merge"):
+                dn = L.name.replace("_merge", "_deconv")
+                if dn in side_set:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    da = self.conv_args[names.index(dn)]
+                    _lib.call("fcn_conv_gemm", C.byref(da), side.cuda_stream)
+                    ev2 = torch.cuda.Event()
+                    ev2.record(side)
+                    joins.append(ev2)
+        if "heads" not in names:
+            for ev in joins:
+                main.wait_event(ev)
 
     def _launch_decode(self, center_ref2):
         eng = self.eng
