@@ -62,7 +62,7 @@ class ConvArgs(C.Structure):
         ("wt", C.c_void_p), ("bias", C.c_void_p), ("w_tc", C.c_void_p),
         ("out", C.c_void_p),
         ("ld_out", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int), ("round_out", C.c_int),
-        ("dbg_clocks", C.c_void_p),
+        ("dbg_clocks", C.c_void_p), ("tmaps", C.c_void_p),
     ]
 
 
@@ -80,6 +80,7 @@ SIGNATURES = {
     "fcn_bct_to_btc": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
+    "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
 }
 
 _lib = None

@@ -7,6 +7,7 @@ int pointnet_tiles_simt(const fcn_pointnet_args &a, cudaStream_t stream);
 int pointnet_tiles_tc(const fcn_pointnet_args &a, cudaStream_t stream);
 int conv_gemm_simt(const fcn_conv_args &a, cudaStream_t stream);
 int conv_gemm_tc(const fcn_conv_args &a, cudaStream_t stream);
+int conv_gemm_tma(const fcn_conv_args &a, cudaStream_t stream);
 }  // namespace fcn
 
 using namespace fcn;
@@ -49,5 +50,6 @@ extern "C" int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream) {
     FCN_REQUIRE(a.wt && a.bias && a.out, "NULL pointer");
     if (a.precision == 0) return conv_gemm_simt(a, (cudaStream_t)stream);
     if (a.precision == 1 || a.precision == 2) return conv_gemm_tc(a, (cudaStream_t)stream);
-    return invalid(__func__, "precision must be 0 (fp32 SIMT), 1 (TF32, N tile 128) or 2 (TF32, N tile 64)");
+    if (a.precision == 3 || a.precision == 4) return conv_gemm_tma(a, (cudaStream_t)stream);
+    return invalid(__func__, "precision must be 0 (fp32 SIMT), 1|2 (TF32 cp.async gather) or 3|4 (TF32 TMA)");
 }

@@ -17,6 +17,7 @@ The sequence of C-ABI calls mirrors PointNetDet.forward (det_base.py:334-412):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
@@ -93,6 +94,7 @@ class FrustumEngine:
         self.num_size = DATASET_INFO[dataset].NUM_SIZE_CLUSTER
         self.device = torch.device(device)
         self.precision = int(precision)
+        self.use_tma = os.environ.get("FCN_CONV_TMA", "1") != "0"   # conv A operand via TMA tensor maps
         self.tile_rows = 64 if self.precision == 0 else 128
         self.out_size = reg_out_size(dataset, self.num_bins)
         self.ld_logit = _round_up(2 + self.out_size, 64)
@@ -325,6 +327,7 @@ class _Plan:
             a.out = _ptr(self.buf["feat%d" % (s + 1)])
             self.pn_args.append(a)
         self.conv_args = []
+        self._tmaps = []
         for L in eng.layers:
             a = _lib.ConvArgs()
             out = self.buf[L.out]
@@ -343,8 +346,19 @@ class _Plan:
                 # The A operand (LDGSTS gather, ~37 B/clk/SM measured) is the feed limit, so the wider
                 # N tile (2x the MMA work per gathered A byte) wins whenever the layer has >= 128 columns.
                 nt = 128 if L.n_cols % 128 == 0 else 64
-                a.precision = 1 if nt == 128 else 2
                 a.w_tc = _ptr(L.tc_image(nt))
+                if eng.use_tma:
+                    # fully TMA-fed variant: one 128-byte tensor map per A segment (host memory, kept alive here)
+                    maps = (C.c_ubyte * (128 * a.n_seg))()
+                    for j, (src, c, tap, st) in enumerate(L.segs):
+                        t = self.buf[src]
+                        _lib.call("fcn_encode_activation_map", C.addressof(maps) + 128 * j, _ptr(t),
+                                  self.B, t.shape[1], t.shape[2], st)
+                    self._tmaps.append(maps)
+                    a.tmaps = C.addressof(maps)
+                    a.precision = 3 if nt == 128 else 4
+                else:
+                    a.precision = 1 if nt == 128 else 2
             a.round_out = 1 if (eng.precision == 1 and L.name != "heads") else 0
             a.wt, a.bias = _ptr(L.wt), _ptr(L.bias)
             a.out, a.ld_out, a.T_store, a.c_off = _ptr(out), out.shape[2], out.shape[1], L.c_off

@@ -122,6 +122,8 @@ FCN_API int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t strea
  *     position-major activations.  Replaces every Conv1d/DeConv1d block of ConvFeatNet
  *     (models/det_base.py:167-224, factories models/common.py:38-63), the torch.cat calls
  *     (multi-segment A operand) and the two heads (det_base.py:367-368).
+ *       precision: 0 fp32 SIMT | 1,2 TF32 tcgen05 with cp.async gather (N tile 128|64) |
+ *                  3,4 TF32 tcgen05 fully TMA-fed (N tile 128|64, needs `tmaps`)
  *       out[b, t*up + j, c_off + co] = act( sum_seg sum_c src[b, t*stride + tap, c] * W + bias )
  *     K is the concatenation of the segments, each padded to a multiple of 32 (zero weights); K_pad
  *     is that sum, optionally rounded up to a multiple of 64 (required by the tensor-core variants).
@@ -141,8 +143,16 @@ typedef struct {
     int ld_out, T_store, c_off;
     int round_out;   /* 1: round outputs to TF32 (cvt.rna) because a tensor-core GEMM consumes them */
     long long *dbg_clocks; /* optional (NULL): CTA (0,0) dumps per-K-block pipeline timestamps, 8 per K block */
+    const void *tmaps;     /* HOST pointer to n_seg 128-byte tensor maps (precision 3|4), see below */
 } fcn_conv_args;
 FCN_API int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream);
+
+/* TMA descriptor of a position-major activation map (B,T,ld) fp32 for the fully TMA-fed conv GEMM
+ * (precision 3 = N tile 128, 4 = N tile 64): 3-D tensor (channel, position, frustum), box
+ * 32 x 128 x 1 with 128-byte swizzle, position step t_stride (1, or 2 for the stride-2 convs).
+ * Writes 128 bytes to HOST memory; pass an array of them (one per segment) in fcn_conv_args.tmaps. */
+FCN_API int fcn_encode_activation_map(void *out_map_128B, const float *base, int B, int T, int ld,
+                                      int t_stride);
 
 /* ------------------------------------------------------------------------------------------
  * (5) Eval decode of the head logits.  Replaces models/det_base.py:376-411 and
