@@ -180,9 +180,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="car", choices=list(ALGO))
     ap.add_argument("--batch", type=int, default=32, help="frustums per GPU per step")
-    ap.add_argument("--precision", type=int, default=int(os.environ.get("FCN_PRECISION", "0")))
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("FCN_PRECISION", "1")),
+                    help="1: TF32 tensor cores (tcgen05) — the arithmetic cuDNN uses by default; 0: fp32 FMA")
     ap.add_argument("--pool-mb", type=float, default=160.0, help="distinct input pool size (> L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "2")),
+                    help="forwards in flight: steps are issued round-robin on this many CUDA streams")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -230,16 +233,37 @@ def main():
         dev_pool.append({k: v.to(dev) for k, v in hb.items()})
     T = [one["center_ref%d" % (i + 1)].shape[2] for i in range(S)]
 
+    # `--streams` forwards in flight: step i runs on stream i % S with its own workspace + CUDA graph
+    # (independent batches; the SM-starved FCN layers of one batch overlap the PointNet tiles of the next)
+    nstream = max(1, args.streams)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstream)]
+    eng = model.engine()
+    plans = []
+    for st in streams:
+        with torch.cuda.stream(st):
+            plans.append(eng.plan(B, one["point_cloud"].shape[2], T))
+    plan = plans[0]
+    if world > 1:
+        gather_bufs = [torch.empty((world,) + tuple(pl.out_flat.shape), dtype=torch.float32, device=dev)
+                       for pl in plans]
+
     def step_resident(i):
-        out = model(dev_pool[i % npool])
-        if world > 1:
-            dist.all_gather_into_tensor(gather_buf, plan.out_flat)
+        k = i % nstream
+        with torch.cuda.stream(streams[k]):
+            out = model(dev_pool[i % npool])
+            if world > 1:
+                dist.all_gather_into_tensor(gather_bufs[k], plans[k].out_flat)
         return out
 
-    eng = model.engine()
-    plan = eng.plan(B, one["point_cloud"].shape[2], T)
-    if world > 1:
-        gather_buf = torch.empty((world,) + tuple(plan.out_flat.shape), dtype=torch.float32, device=dev)
+    def join_streams():
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            cur.wait_stream(st)
+
+    def fork_streams():
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
 
     def barrier():
         if world > 1:
@@ -247,6 +271,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- timed region: inputs resident in HBM
+    t_pre = time.perf_counter()                      # untimed pre-warm: graph capture + clock ramp (~0.3 s)
+    j = 0
+    while time.perf_counter() - t_pre < 0.3 or j < 3 * nstream:
+        step_resident(j)
+        j += 1
+        if j % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     for i in range(args.warmup):
         step_resident(i)
     barrier()
@@ -256,8 +288,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    fork_streams()
     for i in range(args.steps):
         step_resident(args.warmup + i)
+    join_streams()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -270,24 +304,27 @@ def main():
     value = world * B / (ms_step * 1e-3)
 
     # ---- e2e: public API with HOST (pinned) buffers, H2D + D2H inside the timed region
-    host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in plan.out]
-    d2h_bytes = int(sum(o.numel() * 4 for o in host_out))
+    host_outs = [torch.empty(pl.out_flat.shape, dtype=torch.float32).pin_memory() for pl in plans]
+    d2h_bytes = int(host_outs[0].numel() * 4)
 
     def step_e2e(i):
-        hb = host_pool[i % npool]
-        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        out = model(db)
-        for h, o in zip(host_out, out):
-            h.copy_(o, non_blocking=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_buf, plan.out_flat)
+        k = i % nstream
+        with torch.cuda.stream(streams[k]):
+            hb = host_pool[i % npool]
+            db = {kk: v.to(dev, non_blocking=True) for kk, v in hb.items()}   # H2D of this step's inputs
+            model(db)
+            host_outs[k].copy_(plans[k].out_flat, non_blocking=True)           # D2H of the 6-tuple block
+            if world > 1:
+                dist.all_gather_into_tensor(gather_bufs[k], plans[k].out_flat)
 
     for i in range(args.warmup):
         step_e2e(i)
     barrier()
     e0.record()
+    fork_streams()
     for i in range(args.steps):
         step_e2e(args.warmup + i)
+    join_streams()
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -328,7 +365,7 @@ def main():
             "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
             "l2": "inputs cycle through a %d-batch pool (%.0f MB > 126 MB L2); weights/workspaces stay L2-resident"
                   % (npool, npool * step_in_bytes / 1e6),
-            "cuda_graph": True, "precision": roofline["precision"]},
+            "cuda_graph": True, "precision": roofline["precision"], "streams_in_flight": nstream},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step_in_bytes,
                 "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": kt["launches_per_step"] * args.steps,

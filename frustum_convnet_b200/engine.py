@@ -198,10 +198,13 @@ class FrustumEngine:
 
     # ------------------------------------------------------------------ shape plans
     def plan(self, B: int, N: int, T: Sequence[int]) -> "_Plan":
-        key = (int(B), int(N), tuple(int(t) for t in T))
+        """Workspace for one input shape ON THE CURRENT STREAM: forwards issued from different streams
+        (``with torch.cuda.stream(s): model(x)``) get disjoint workspaces/graphs and may overlap."""
+        shape = (int(B), int(N), tuple(int(t) for t in T))
+        key = shape + (torch.cuda.current_stream(self.device).cuda_stream,)
         p = self._plans.get(key)
         if p is None:
-            p = _Plan(self, *key)
+            p = _Plan(self, *shape)
             self._plans[key] = p
         return p
 
