@@ -484,16 +484,21 @@ class _Plan:
             return self.out
 
     def _capture(self):
-        # warm-up run outside capture (sets function attributes, loads modules)
-        self._launch_feat(self.in_pc, self.in_centers, self.in_onehot)
-        self._launch_fcn()
-        self._launch_decode(self.in_centers[1])
+        skip = set(os.environ.get("FCN_DIAG_SKIP", "").split(","))   # timing diagnostics only
+
+        def seq():
+            if "feat" not in skip:
+                self._launch_feat(self.in_pc, self.in_centers, self.in_onehot)
+            if "fcn" not in skip:
+                self._launch_fcn()
+            if "decode" not in skip:
+                self._launch_decode(self.in_centers[1])
+
+        seq()   # warm-up run outside capture (sets function attributes, loads modules)
         torch.cuda.current_stream().synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._launch_feat(self.in_pc, self.in_centers, self.in_onehot)
-            self._launch_fcn()
-            self._launch_decode(self.in_centers[1])
+            seq()
         self.graph = g
 
     def run_feat(self, pc, centers, one_hot):
