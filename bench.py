@@ -224,13 +224,6 @@ def main():
     npool = max(2, int(np.ceil(args.pool_mb * 1e6 / step_in_bytes)))
     ngen = min(npool, 8)   # 8 seeded batches, the rest are per-frustum rotations of them
     base = [synth.make_frustums(args.workload, B, seed=1234 + rank + 1000 * i) for i in range(ngen)]
-    host_pool, dev_pool = [], []
-    for i in range(npool):
-        src = base[i % ngen]
-        sh = (i // ngen) % B
-        hb = {k: torch.from_numpy(np.roll(src[k], sh, axis=0).copy()).pin_memory() for k in keys}
-        host_pool.append(hb)
-        dev_pool.append({k: v.to(dev) for k, v in hb.items()})
     T = [one["center_ref%d" % (i + 1)].shape[2] for i in range(S)]
 
     # `--streams` forwards in flight: step i runs on stream i % S with its own workspace + CUDA graph
@@ -243,6 +236,17 @@ def main():
         with torch.cuda.stream(st):
             plans.append(eng.plan(B, one["point_cloud"].shape[2], T))
     plan = plans[0]
+    # every pool entry is one packed block in the engine's input layout (one staging copy per step)
+    host_pool, dev_pool = [], []
+    for i in range(npool):
+        src = base[i % ngen]
+        sh = (i // ngen) % B
+        hflat, _ = plan.pack({k: np.roll(src[k], sh, axis=0) for k in keys}, pin=True)
+        host_pool.append(hflat)
+        dflat = hflat.to(dev)
+        dviews = {k: dflat[off: off + ref.numel()].view(ref.shape)
+                  for k, off, ref in zip(keys, plan._in_offs, [plan.in_pc] + plan.in_centers + [plan.in_onehot])}
+        dev_pool.append(dviews)
     if world > 1:
         gather_bufs = [torch.empty((world,) + tuple(pl.out_flat.shape), dtype=torch.float32, device=dev)
                        for pl in plans]
@@ -307,12 +311,13 @@ def main():
     host_outs = [torch.empty(pl.out_flat.shape, dtype=torch.float32).pin_memory() for pl in plans]
     d2h_bytes = int(host_outs[0].numel() * 4)
 
+    in_views = [pl.input_views() for pl in plans]
+
     def step_e2e(i):
         k = i % nstream
         with torch.cuda.stream(streams[k]):
-            hb = host_pool[i % npool]
-            db = {kk: v.to(dev, non_blocking=True) for kk, v in hb.items()}   # H2D of this step's inputs
-            model(db)
+            plans[k].in_flat.copy_(host_pool[i % npool], non_blocking=True)    # H2D of this step's inputs
+            model(in_views[k])                                                 # public API, zero-copy staging
             host_outs[k].copy_(plans[k].out_flat, non_blocking=True)           # D2H of the 6-tuple block
             if world > 1:
                 dist.all_gather_into_tensor(gather_bufs[k], plans[k].out_flat)
@@ -366,7 +371,7 @@ def main():
             "l2": "inputs cycle through a %d-batch pool (%.0f MB > 126 MB L2); weights/workspaces stay L2-resident"
                   % (npool, npool * step_in_bytes / 1e6),
             "cuda_graph": True, "precision": roofline["precision"], "streams_in_flight": nstream},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": step_in_bytes,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(plan.in_flat.numel() * 4),
                 "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": kt["launches_per_step"] * args.steps,
         "launches_per_step": kt["launches_per_step"],

@@ -59,6 +59,8 @@ class _EngineOwner(nn.Module):
 
     _engine = None
     _engine_key = None
+    _engine_dirty = True
+    _engine_calls = 0
     precision = 0  # 0: fp32 CUDA cores, 1: TF32 tensor cores for the dense layers
 
     def _engine_spec(self):  # -> (arch, num_vec, dataset, dists, num_bins, prefix)
@@ -68,7 +70,30 @@ class _EngineOwner(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
             tuple((b.data_ptr(), b._version) for b in self.buffers())
 
+    # weight-pack invalidation: mode switches, device moves and load_state_dict mark the pack dirty;
+    # in-place edits of individual parameters are caught by a full version scan every 64th call
+    # (a scan per call costs ~100 us of host time, more than the whole GPU forward).
+    def train(self, mode=True):
+        self._engine_dirty = True
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._engine_dirty = True
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._engine_dirty = True
+        return super().load_state_dict(*args, **kwargs)
+
+    def refresh(self):
+        """Force a rebuild of the kernel-ready weight pack at the next eval forward."""
+        self._engine_dirty = True
+
     def engine(self) -> FrustumEngine:
+        self._engine_calls += 1
+        if self._engine is not None and not self._engine_dirty and (self._engine_calls & 63) and \
+                self._engine.precision == self.precision:
+            return self._engine
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("the frustum hot path runs on CUDA only (no CPU fallback); "
@@ -79,6 +104,7 @@ class _EngineOwner(nn.Module):
             sd = {prefix + k: v for k, v in self.state_dict().items()}
             self._engine = FrustumEngine(arch, num_vec, dataset, dists, num_bins, sd, dev, self.precision)
             self._engine_key = key
+        self._engine_dirty = False
         return self._engine
 
 
