@@ -307,6 +307,14 @@ def main():
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
+    # host-side issue cost per step (queue empty, no waiting on the GPU): shows whether the loop is CPU-bound
+    torch.cuda.synchronize()
+    t_h = time.perf_counter()
+    for i in range(32):
+        step_resident(i)
+    host_us = (time.perf_counter() - t_h) / 32 * 1e6
+    torch.cuda.synchronize()
+
     # ---- e2e: public API with HOST (pinned) buffers, H2D + D2H inside the timed region
     host_outs = [torch.empty(pl.out_flat.shape, dtype=torch.float32).pin_memory() for pl in plans]
     d2h_bytes = int(host_outs[0].numel() * 4)
@@ -373,6 +381,7 @@ def main():
             "cuda_graph": True, "precision": roofline["precision"], "streams_in_flight": nstream},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(plan.in_flat.numel() * 4),
                 "d2h_bytes_per_step": d2h_bytes},
+        "host_issue_us_per_step": host_us,
         "gpu_launches": kt["launches_per_step"] * args.steps,
         "launches_per_step": kt["launches_per_step"],
         "roofline": roofline, "hbm": hbm, "clocks": clocks,
