@@ -22,7 +22,8 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_COMPUTE_WARPS = 8;
 constexpr int TC_THREADS = (TC_COMPUTE_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 16384;
-constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 32 rows x 32 columns per warp
+constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 16 rows x 32 columns per warp (two passes)
+constexpr int TC_SLAB_ROWS = 16;
 constexpr int TC_SLAB_LD = TC_SLAB_COLS + 4;  // +4 floats: conflict-free float4 row writes / column reads
 
 __device__ __forceinline__ bool elect_one() {
@@ -41,7 +42,7 @@ struct TcCfg {
     static constexpr int NCH3 = C3 / N3;
     static constexpr int A_BYTES = TC_ROWS * (C1 > C2 ? C1 : C2) * 4;
     static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
-    static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 6 : JOBS);
+    static constexpr int NSTAGE = (C1 >= 256) ? 4 : (C1 >= 128 ? 8 : JOBS);
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
     static constexpr int OFF_W = A_BYTES;
     static constexpr int OFF_RECS = OFF_W + NSTAGE * TC_STAGE_BYTES;
@@ -50,7 +51,7 @@ struct TcCfg {
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;                 // int sect[128]
     static constexpr int OFF_SLAB = OFF_SECT + 2 * TC_ROWS * 4;      // per-warp [32][TC_SLAB_LD] fp32
-    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * 32 * TC_SLAB_LD * 4;
+    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * TC_SLAB_ROWS * TC_SLAB_LD * 4;
     static constexpr int NBAR = 2 * NSTAGE + KBMAX + 1 + 4;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
@@ -131,14 +132,21 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
         constexpr uint32_t idesc3 = make_idesc_tf32(128, Cfg::N3);
         const uint64_t adesc0 = make_desc_sw128(sA_addr), bdesc0 = make_desc_sw128(sW_addr);
         uint32_t job = 0, chunk = 0;
+        bool w_ready = false;
+        // non-blocking look-ahead at the weight stage of job j (resident weights: always there after tile 0)
+        auto probe_next = [&](uint32_t j) -> bool {
+            if (Cfg::RESIDENT) return j >= (uint32_t)Cfg::JOBS || mbar_try_wait(&w_full[j % Cfg::NSTAGE], 0);
+            return mbar_try_wait(&w_full[j % Cfg::NSTAGE], (j / Cfg::NSTAGE) & 1);
+        };
         for (int it = 0; it < my_tiles; ++it) {
-            if (Cfg::RESIDENT) job = 0;
+            if (Cfg::RESIDENT) { job = 0; w_ready = it > 0; }
             // ---- layer 2
             for (int nc = 0; nc < Cfg::NCH2; ++nc) {
                 for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
                     if (nc == 0) mbar_wait(&a_ready[kb], 0);
-                    mbar_wait(&w_full[st], ph);
+                    if (!w_ready) mbar_wait(&w_full[st], ph);
+                    w_ready = probe_next(job + 1);   // issued before the MMAs: its latency hides behind them
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
@@ -161,7 +169,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
                     if (nc == 0) mbar_wait(&a_ready[kb], 1);
-                    mbar_wait(&w_full[st], ph);
+                    if (!w_ready) mbar_wait(&w_full[st], ph);
+                    w_ready = probe_next(job + 1);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
@@ -185,21 +194,28 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
         const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const int rx = row & 7;
         uint32_t chunk = 0;
+        int4 td_next = tiles[blockIdx.x];
+        float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h == 0 && row < td_next.z)
+            rec_next = ((const float4 *)p.rows + (size_t)td_next.x * p.row_cap + td_next.y)[row];
         for (int it = 0; it < my_tiles; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int4 td = tiles[tile];
-            const int b = td.x, row0 = td.y, nrows = td.z;
-            const float4 *grows = (const float4 *)p.rows + (size_t)b * p.row_cap + row0;
+            const int4 td = td_next;           // tile descriptor + this thread's record were prefetched
+            const int b = td.x, nrows = td.z;  // during the previous tile (two dependent global loads)
             // staging buffers alternate with the tile parity: a warp that runs ahead into tile it+1
             // must not overwrite what slower warps still read for tile it (they meet at this barrier)
             float4 *recs = recs_all + (it & 1) * TC_ROWS;
             int *sect_s = sect_all + (it & 1) * TC_ROWS;
-            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 rec = rec_next;
             const bool valid = row < nrows;
             if (h == 0) {
-                if (valid) rec = grows[row];
                 recs[row] = rec;
                 sect_s[row] = __float_as_int(rec.w) & 0x7fffffff;
+            }
+            if (it + 1 < my_tiles) {
+                td_next = tiles[blockIdx.x + (it + 1) * gridDim.x];
+                rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (h == 0 && row < td_next.z)
+                    rec_next = ((const float4 *)p.rows + (size_t)td_next.x * p.row_cap + td_next.y)[row];
             }
             asm volatile("bar.sync 1, %0;\n" ::"n"(TC_COMPUTE_WARPS * 32));
             rec = recs[row];
@@ -253,7 +269,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             //      rows, then +bias, ReLU and a coalesced integer atomicMax into the feature map
             //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
-            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * TC_SLAB_LD);
+            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (TC_SLAB_ROWS * TC_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
                 const uint32_t buf = chunk & 1;
                 mbar_wait(&acc3_full[buf], (chunk >> 1) & 1);
@@ -264,29 +280,41 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     uint32_t v[32];
                     tmem_ld32(lane_taddr + 256 + buf * 128 + col0, v);
                     tmem_wait_ld();
-#pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4)
-                        *(uint4 *)(slab + lane * TC_SLAB_LD + c4 * 4) =
-                            make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                    __syncwarp();
-                    // lane = column; the warp walks its rows section by section (bounds are warp-uniform)
+                    // lane = column; the warp walks its 32 rows section by section (bounds are warp-uniform)
+                    // through a 16-row slab in two passes; the running max carries across the passes
                     const int c = nc * Cfg::N3 + col0 + lane;
                     const float bias = b3s[c];
                     const float *col = slab + lane;
-                    unsigned em = endmask;
-                    int start = 0;
-                    while (em) {
-                        const int end = __ffs(em) - 1;
-                        em &= em - 1;
-                        float run = col[start * TC_SLAB_LD];
+                    float run = -INFINITY;
+#pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if ((lane >> 4) == pass) {
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4)
+                                *(uint4 *)(slab + (lane & 15) * TC_SLAB_LD + c4 * 4) =
+                                    make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                        }
+                        __syncwarp();
+                        unsigned em = (endmask >> (16 * pass)) & 0xffffu;
+                        int start = 0;
+                        while (em) {
+                            const int end = __ffs(em) - 1;
+                            em &= em - 1;
 #pragma unroll 4
-                        for (int r = start + 1; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
-                        const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
-                        if (o > 0.f)
-                            atomicMax(feat + (size_t)sect_s[q * 32 + end] * p.ld_feat + c, __float_as_int(o));
-                        start = end + 1;
+                            for (int r = start; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                            const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
+                            if (o > 0.f)
+                                atomicMax(feat + (size_t)sect_s[q * 32 + 16 * pass + end] * p.ld_feat + c,
+                                          __float_as_int(o));
+                            run = -INFINITY;
+                            start = end + 1;
+                        }
+                        // rows after the last section end of this pass belong to a section that continues in
+                        // the next pass (or are padding rows that are never flushed)
+#pragma unroll 4
+                        for (int r = start; r < 16; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();
