@@ -135,8 +135,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
         bool w_ready = false;
         // non-blocking look-ahead at the weight stage of job j (resident weights: always there after tile 0)
         auto probe_next = [&](uint32_t j) -> bool {
-            if (Cfg::RESIDENT) return j >= (uint32_t)Cfg::JOBS || mbar_try_wait(&w_full[j % Cfg::NSTAGE], 0);
-            return mbar_try_wait(&w_full[j % Cfg::NSTAGE], (j / Cfg::NSTAGE) & 1);
+            if (Cfg::RESIDENT) return j >= (uint32_t)Cfg::JOBS || mbar_test_wait(&w_full[j % Cfg::NSTAGE], 0);
+            return mbar_test_wait(&w_full[j % Cfg::NSTAGE], (j / Cfg::NSTAGE) & 1);
         };
         for (int it = 0; it < my_tiles; ++it) {
             if (Cfg::RESIDENT) { job = 0; w_ready = it > 0; }
