@@ -22,8 +22,8 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_COMPUTE_WARPS = 8;
 constexpr int TC_THREADS = (TC_COMPUTE_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 16384;
-constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 16 rows x 32 columns per warp (two passes)
-constexpr int TC_SLAB_ROWS = 16;
+constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 32 rows x 32 columns per warp
+constexpr int TC_SLAB_ROWS = 32;
 constexpr int TC_SLAB_LD = TC_SLAB_COLS + 4;  // +4 floats: conflict-free float4 row writes / column reads
 
 __device__ __forceinline__ bool elect_one() {
@@ -42,7 +42,7 @@ struct TcCfg {
     static constexpr int NCH3 = C3 / N3;
     static constexpr int A_BYTES = TC_ROWS * (C1 > C2 ? C1 : C2) * 4;
     static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
-    static constexpr int NSTAGE = (C1 >= 256) ? 4 : (C1 >= 128 ? 8 : JOBS);
+    static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 6 : JOBS);
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
     static constexpr int OFF_W = A_BYTES;
     static constexpr int OFF_RECS = OFF_W + NSTAGE * TC_STAGE_BYTES;
@@ -281,40 +281,28 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     tmem_ld32(lane_taddr + 256 + buf * 128 + col0, v);
                     tmem_wait_ld();
                     // lane = column; the warp walks its 32 rows section by section (bounds are warp-uniform)
-                    // through a 16-row slab in two passes; the running max carries across the passes
                     const int c = nc * Cfg::N3 + col0 + lane;
                     const float bias = b3s[c];
                     const float *col = slab + lane;
-                    float run = -INFINITY;
-#pragma unroll 1
-                    for (int pass = 0; pass < 2; ++pass) {
-                        if ((lane >> 4) == pass) {
 #pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4)
-                                *(uint4 *)(slab + (lane & 15) * TC_SLAB_LD + c4 * 4) =
-                                    make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                        }
-                        __syncwarp();
-                        unsigned em = (endmask >> (16 * pass)) & 0xffffu;
-                        int start = 0;
-                        while (em) {
-                            const int end = __ffs(em) - 1;
-                            em &= em - 1;
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *(uint4 *)(slab + lane * TC_SLAB_LD + c4 * 4) =
+                            make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                    __syncwarp();
+                    unsigned em = endmask;
+                    int start = 0;
+                    while (em) {
+                        const int end = __ffs(em) - 1;
+                        em &= em - 1;
+                        float run = col[start * TC_SLAB_LD];
 #pragma unroll 4
-                            for (int r = start; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
-                            const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
-                            if (o > 0.f)
-                                atomicMax(feat + (size_t)sect_s[q * 32 + 16 * pass + end] * p.ld_feat + c,
-                                          __float_as_int(o));
-                            run = -INFINITY;
-                            start = end + 1;
-                        }
-                        // rows after the last section end of this pass belong to a section that continues in
-                        // the next pass (or are padding rows that are never flushed)
-#pragma unroll 4
-                        for (int r = start; r < 16; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
-                        __syncwarp();
+                        for (int r = start + 1; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                        const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
+                        if (o > 0.f)
+                            atomicMax(feat + (size_t)sect_s[q * 32 + end] * p.ld_feat + c, __float_as_int(o));
+                        start = end + 1;
                     }
+                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();
