@@ -44,7 +44,7 @@ class PointnetArgs(C.Structure):
         ("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
         ("w3t", C.c_void_p), ("b3", C.c_void_p),
         ("w2_tc", C.c_void_p), ("w3_tc", C.c_void_p),
-        ("out", C.c_void_p),
+        ("out", C.c_void_p), ("dbg_clocks", C.c_void_p),
     ]
 
 

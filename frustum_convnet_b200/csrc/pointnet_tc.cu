@@ -138,15 +138,21 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             if (Cfg::RESIDENT) return j >= (uint32_t)Cfg::JOBS || mbar_test_wait(&w_full[j % Cfg::NSTAGE], 0);
             return mbar_test_wait(&w_full[j % Cfg::NSTAGE], (j / Cfg::NSTAGE) & 1);
         };
+        const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && lane == 0;
+        uint32_t dj = 0;   // debug job counter (never reset)
         for (int it = 0; it < my_tiles; ++it) {
             if (Cfg::RESIDENT) { job = 0; w_ready = it > 0; }
             // ---- layer 2
             for (int nc = 0; nc < Cfg::NCH2; ++nc) {
                 for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
+                    long long t0 = 0, t1 = 0, t2 = 0;
+                    if (dbg) t0 = clock64();
                     if (nc == 0) mbar_wait(&a_ready[kb], 0);
+                    if (dbg) t1 = clock64();
                     if (!w_ready) mbar_wait(&w_full[st], ph);
                     w_ready = probe_next(job + 1);   // issued before the MMAs: its latency hides behind them
+                    if (dbg) t2 = clock64();
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
@@ -157,6 +163,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
                     }
                     __syncwarp();
+                    if (dbg && dj < 1000) { long long *d = p.dbg_clocks + 4 * dj; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
+                    ++dj;
                 }
             }
             if (elect_one()) mma_commit(acc2_full);
@@ -168,9 +176,13 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 tc_fence_after();
                 for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
+                    long long t0 = 0, t1 = 0, t2 = 0;
+                    if (dbg) t0 = clock64();
                     if (nc == 0) mbar_wait(&a_ready[kb], 1);
+                    if (dbg) t1 = clock64();
                     if (!w_ready) mbar_wait(&w_full[st], ph);
                     w_ready = probe_next(job + 1);
+                    if (dbg) t2 = clock64();
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
@@ -181,6 +193,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
                     }
                     __syncwarp();
+                    if (dbg && dj < 1000) { long long *d = p.dbg_clocks + 4 * dj; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
+                    ++dj;
                 }
                 if (elect_one()) mma_commit(&acc3_full[buf]);
                 __syncwarp();
@@ -198,7 +212,10 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
         float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
         if (h == 0 && row < td_next.z)
             rec_next = ((const float4 *)p.rows + (size_t)td_next.x * p.row_cap + td_next.y)[row];
+        const bool dbgc = p.dbg_clocks != nullptr && blockIdx.x == 0 && tid == 0;
         for (int it = 0; it < my_tiles; ++it) {
+            long long *dc = p.dbg_clocks + 4096 + 16 * it;
+            if (dbgc) dc[0] = clock64();
             const int4 td = td_next;           // tile descriptor + this thread's record were prefetched
             const int b = td.x, nrows = td.z;  // during the previous tile (two dependent global loads)
             // staging buffers alternate with the tile parity: a warp that runs ahead into tile it+1
@@ -219,6 +236,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             }
             asm volatile("bar.sync 1, %0;\n" ::"n"(TC_COMPUTE_WARPS * 32));
             rec = recs[row];
+            if (dbgc) dc[1] = clock64();
             const int sect = __float_as_int(rec.w) & 0x7fffffff;
             // section bookkeeping of this warp's 32 rows (rows are section-sorted): bit r of endmask
             // is set when row r is the last valid row of its section inside this warp
@@ -244,7 +262,9 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 if (lane == 0) mbar_arrive(&a_ready[kb]);
             }
             // ---- epilogue 2: TMEM -> +bias, ReLU, TF32 -> A2 (same buffer; all layer-2 MMAs are done)
+            if (dbgc) dc[2] = clock64();
             mbar_wait(acc2_full, it & 1);
+            if (dbgc) dc[3] = clock64();
             tc_fence_after();
             for (int kb = h; kb < Cfg::KB2; kb += 2) {
                 uint32_t v[32];
@@ -268,11 +288,13 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             //      slabs through per-warp shared memory (thread = column), running max over the section's
             //      rows, then +bias, ReLU and a coalesced integer atomicMax into the feature map
             //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
+            if (dbgc) dc[4] = clock64();
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
             float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (TC_SLAB_ROWS * TC_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
                 const uint32_t buf = chunk & 1;
                 mbar_wait(&acc3_full[buf], (chunk >> 1) & 1);
+                if (dbgc && nc < 5) dc[5 + 2 * nc] = clock64();
                 tc_fence_after();
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
@@ -306,6 +328,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
                 tc_fence_before();
                 __syncwarp();
+                if (dbgc && nc < 5) dc[6 + 2 * nc] = clock64();
                 if (lane == 0) mbar_arrive(&acc3_empty[buf]);
             }
         }

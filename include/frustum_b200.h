@@ -114,6 +114,7 @@ typedef struct {
     const float *w1t, *b1, *w2t, *b2, *w3t, *b3;
     const void *w2_tc, *w3_tc;  /* tensor-core packed images (precision=1), else NULL */
     float *out;
+    long long *dbg_clocks;  /* optional (NULL): CTA 0 dumps pipeline timestamps (diagnostics) */
 } fcn_pointnet_args;
 FCN_API int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t stream);
 
