@@ -186,7 +186,12 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
                         long long t0 = 0, t1 = 0, t2 = 0;
                         if (dbg) t0 = clock64();
-                        if (pp == 0) mbar_wait(&a_ready[kb], 1);
+                        if (pp == 0) {
+                            // an issuer without layer-2 work still has to pass the A1 phase of this tile first,
+                            // otherwise the parity-1 wait is satisfied by the previous tile's A2 phase
+                            if (me >= Cfg::NI2) mbar_wait(&a_ready[kb], 0);
+                            mbar_wait(&a_ready[kb], 1);
+                        }
                         if (dbg) t1 = clock64();
                         if (!skip_w_wait) mbar_wait(&w_full[st], ph);
                         if (dbg) t2 = clock64();
