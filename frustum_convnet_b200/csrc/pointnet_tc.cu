@@ -56,7 +56,7 @@ struct TcCfg {
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;                 // int sect[128]
     static constexpr int OFF_SLAB = OFF_SECT + 2 * TC_ROWS * 4;      // per-warp [32][TC_SLAB_LD] fp32
     static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * TC_SLAB_ROWS * TC_SLAB_LD * 4;
-    static constexpr int NBAR = 2 * NSTAGE + KBMAX + 1 + 4;
+    static constexpr int NBAR = 2 * NSTAGE + 2 * KBMAX + 1 + 4;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
     static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 128 == 0, "channel counts");
@@ -80,8 +80,11 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     int *sect_all = (int *)(smem + Cfg::OFF_SECT);
     uint64_t *bars = (uint64_t *)(smem + Cfg::OFF_BAR);
     uint64_t *w_full = bars, *w_empty = bars + Cfg::NSTAGE;
-    uint64_t *a_ready = bars + 2 * Cfg::NSTAGE;
-    uint64_t *acc2_full = a_ready + Cfg::KBMAX;
+    // A-operand K-block barriers, one set per use (A1 = layer-1 output, A2 = layer-2 output): each
+    // completes exactly once per tile, so waiters use parity (tile & 1) and can never lap a phase
+    uint64_t *a1_ready = bars + 2 * Cfg::NSTAGE;
+    uint64_t *a2_ready = a1_ready + Cfg::KBMAX;
+    uint64_t *acc2_full = a2_ready + Cfg::KBMAX;
     uint64_t *acc3_full = acc2_full + 1, *acc3_empty = acc3_full + 2;
     uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
 
@@ -99,7 +102,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     for (int i = tid; i < C3; i += TC_THREADS) b3s[i] = __ldg(p.b3 + i);
     if (tid == 0) {
         for (int i = 0; i < Cfg::NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < Cfg::KBMAX; ++i) mbar_init(&a_ready[i], 4);
+        for (int i = 0; i < Cfg::KBMAX; ++i) { mbar_init(&a1_ready[i], 4); mbar_init(&a2_ready[i], 4); }
         mbar_init(acc2_full, Cfg::NI2);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc3_full[i], 1); mbar_init(&acc3_empty[i], TC_COMPUTE_WARPS); }
         fence_barrier_init();
@@ -154,7 +157,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
                     long long t0 = 0, t1 = 0, t2 = 0;
                     if (dbg) t0 = clock64();
-                    mbar_wait(&a_ready[kb], 0);
+                    mbar_wait(&a1_ready[kb], it & 1);
                     if (dbg) t1 = clock64();
                     if (!skip_w_wait) mbar_wait(&w_full[st], ph);
                     if (dbg) t2 = clock64();
@@ -186,12 +189,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
                         long long t0 = 0, t1 = 0, t2 = 0;
                         if (dbg) t0 = clock64();
-                        if (pp == 0) {
-                            // an issuer without layer-2 work still has to pass the A1 phase of this tile first,
-                            // otherwise the parity-1 wait is satisfied by the previous tile's A2 phase
-                            if (me >= Cfg::NI2) mbar_wait(&a_ready[kb], 0);
-                            mbar_wait(&a_ready[kb], 1);
-                        }
+                        if (pp == 0) mbar_wait(&a2_ready[kb], it & 1);
                         if (dbg) t1 = clock64();
                         if (!skip_w_wait) mbar_wait(&w_full[st], ph);
                         if (dbg) t2 = clock64();
@@ -273,7 +271,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[kb]);
+                if (lane == 0) mbar_arrive(&a1_ready[kb]);
             }
             // ---- epilogue 2: TMEM -> +bias, ReLU, TF32 -> A2 (same buffer; all layer-2 MMAs are done)
             if (dbgc) dc[2] = clock64();
@@ -296,7 +294,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[kb]);
+                if (lane == 0) mbar_arrive(&a2_ready[kb]);
             }
             // ---- epilogue 3: per 128-column chunk: TMEM -> registers (thread = row), transpose 16-column
             //      slabs through per-warp shared memory (thread = column), running max over the section's
