@@ -397,6 +397,10 @@ class _Plan:
         S = len(self.pn_args)
         if S == 0:
             return
+        if os.environ.get("FCN_NO_FORK", "0") == "1":      # diagnostics: everything on one stream
+            for s_ in range(S - 1, -1, -1):
+                _lib.call("fcn_pointnet_tiles", C.byref(self.pn_args[s_]), main.cuda_stream)
+            return
         side = self._side_streams(S - 1)
         fork = torch.cuda.Event()
         fork.record(main)
