@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <utility>
 
 #include "../../include/frustum_b200.h"
@@ -63,8 +64,9 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("FCN_NO_PDL") != nullptr;   // diagnostics
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
