@@ -6,9 +6,6 @@
 #include "umma.cuh"
 
 namespace fcn {
-namespace umma {
-__device__ long long *g_trap_info = nullptr;
-}
 using namespace umma;
 
 template <int N>
@@ -85,10 +82,5 @@ extern "C" int fcn_selftest_umma(int N, int K, const float *A, const void *w_img
         umma_selftest_kernel<128><<<1, 128, smem, (cudaStream_t)stream>>>(K, A, (const uint8_t *)w_img, D);
     }
     FCN_LAUNCH_CHECK();
-    return FCN_OK;
-}
-
-extern "C" int fcn_set_trap_buffer(long long *host_mapped_device_ptr) {
-    FCN_CUDA(cudaMemcpyToSymbol(fcn::umma::g_trap_info, &host_mapped_device_ptr, sizeof(long long *)));
     return FCN_OK;
 }

@@ -59,8 +59,8 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.  When a
 // host-mapped diagnostics buffer was registered (fcn_set_trap_buffer) the stuck barrier is recorded first.
-extern __device__ long long *g_trap_info;
-__device__ __noinline__ void mbar_timeout(uint64_t *bar, uint32_t parity) {
+static __device__ long long *g_trap_info = nullptr;   // one copy per translation unit (no -rdc)
+static __device__ __noinline__ void mbar_timeout(uint64_t *bar, uint32_t parity) {
     if (g_trap_info != nullptr) {
         g_trap_info[0] = 0x7AB0;
         g_trap_info[1] = smem_u32(bar);
