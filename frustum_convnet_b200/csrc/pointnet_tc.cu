@@ -20,8 +20,7 @@ using namespace umma;
 
 constexpr int TC_ROWS = 128;
 constexpr int TC_COMPUTE_WARPS = 8;
-constexpr int TC_ISSUE_WARPS = 2;              // two MMA-issuing warps work on different N chunks (see below)
-constexpr int TC_THREADS = (TC_COMPUTE_WARPS + TC_ISSUE_WARPS + 1) * 32;
+constexpr int TC_THREADS = (TC_COMPUTE_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 32 rows x 32 columns per warp
 constexpr int TC_SLAB_ROWS = 32;
@@ -43,9 +42,6 @@ struct TcCfg {
     static constexpr int NCH3 = C3 / N3;
     static constexpr int A_BYTES = TC_ROWS * (C1 > C2 ? C1 : C2) * 4;
     static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
-    static constexpr int NI2 = NCH2 >= 2 ? 2 : 1;     // MMA issuers active in layer 2
-    static constexpr int NQ = NCH3 >= 2 ? 2 : 1;      // ... in layer 3 (chunk c belongs to issuer c & 1)
-    static_assert(NCH2 <= 2 && NCH3 % NQ == 0, "chunk -> issuer mapping");
     static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 6 : JOBS);
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
     static constexpr int OFF_W = A_BYTES;
@@ -56,7 +52,7 @@ struct TcCfg {
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;                 // int sect[128]
     static constexpr int OFF_SLAB = OFF_SECT + 2 * TC_ROWS * 4;      // per-warp [32][TC_SLAB_LD] fp32
     static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * TC_SLAB_ROWS * TC_SLAB_LD * 4;
-    static constexpr int NBAR = 2 * NSTAGE + 2 * KBMAX + 1 + 4;
+    static constexpr int NBAR = 2 * NSTAGE + KBMAX + 1 + 4;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
     static_assert(C1 % 32 == 0 && C2 % 32 == 0 && C3 % 128 == 0, "channel counts");
@@ -80,11 +76,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     int *sect_all = (int *)(smem + Cfg::OFF_SECT);
     uint64_t *bars = (uint64_t *)(smem + Cfg::OFF_BAR);
     uint64_t *w_full = bars, *w_empty = bars + Cfg::NSTAGE;
-    // A-operand K-block barriers, one set per use (A1 = layer-1 output, A2 = layer-2 output): each
-    // completes exactly once per tile, so waiters use parity (tile & 1) and can never lap a phase
-    uint64_t *a1_ready = bars + 2 * Cfg::NSTAGE;
-    uint64_t *a2_ready = a1_ready + Cfg::KBMAX;
-    uint64_t *acc2_full = a2_ready + Cfg::KBMAX;
+    uint64_t *a_ready = bars + 2 * Cfg::NSTAGE;
+    uint64_t *acc2_full = a_ready + Cfg::KBMAX;
     uint64_t *acc3_full = acc2_full + 1, *acc3_empty = acc3_full + 2;
     uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
 
@@ -102,8 +95,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     for (int i = tid; i < C3; i += TC_THREADS) b3s[i] = __ldg(p.b3 + i);
     if (tid == 0) {
         for (int i = 0; i < Cfg::NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < Cfg::KBMAX; ++i) { mbar_init(&a1_ready[i], 4); mbar_init(&a2_ready[i], 4); }
-        mbar_init(acc2_full, Cfg::NI2);
+        for (int i = 0; i < Cfg::KBMAX; ++i) mbar_init(&a_ready[i], 4);
+        mbar_init(acc2_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc3_full[i], 1); mbar_init(&acc3_empty[i], TC_COMPUTE_WARPS); }
         fence_barrier_init();
     }
@@ -115,7 +108,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
     const int4 *tiles = (const int4 *)p.tiles;
 
-    if (warp == TC_COMPUTE_WARPS + TC_ISSUE_WARPS) {
+    if (warp == TC_COMPUTE_WARPS + 1) {
         // ================= weight loader (one elected lane) =================
         if (lane == 0) {
             const int ntile_loads = Cfg::RESIDENT ? 1 : my_tiles;
@@ -133,33 +126,32 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
             }
         }
-    } else if (warp >= TC_COMPUTE_WARPS) {
-        // ================= MMA issuers: warp-uniform control flow, an elected lane issues =================
-        // Measured: one thread issues a tcgen05.mma every ~60 clk and pays ~100 clk per mbarrier wait, i.e.
-        // ~480 clk per 4-MMA job whose math is 256 clk.  Two issuer warps therefore walk the same job
-        // sequence and each takes the jobs of "its" N chunks (chunk parity == issuer id): the accumulators
-        // are disjoint TMEM regions, so no ordering between the two is needed, and one warp's bookkeeping
-        // overlaps the other's MMAs.
-        const int me = warp - TC_COMPUTE_WARPS;
+    } else if (warp == TC_COMPUTE_WARPS) {
+        // ================= MMA issuer: warp-uniform control flow, elected lane issues =================
         constexpr uint32_t idesc2 = make_idesc_tf32(128, Cfg::N2);
         constexpr uint32_t idesc3 = make_idesc_tf32(128, Cfg::N3);
         const uint64_t adesc0 = make_desc_sw128(sA_addr), bdesc0 = make_desc_sw128(sW_addr);
-        const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && lane == 0 && me == 0;
-        uint32_t dj = 0, use = 0;   // debug job counter; uses of this issuer's acc3 buffer
+        uint32_t job = 0, chunk = 0;
+        bool w_ready = false;
+        // non-blocking look-ahead at the weight stage of job j (resident weights: always there after tile 0)
+        auto probe_next = [&](uint32_t j) -> bool {
+            if (Cfg::RESIDENT) return j >= (uint32_t)Cfg::JOBS || mbar_test_wait(&w_full[j % Cfg::NSTAGE], 0);
+            return mbar_test_wait(&w_full[j % Cfg::NSTAGE], (j / Cfg::NSTAGE) & 1);
+        };
+        const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && lane == 0;
+        uint32_t dj = 0;   // debug job counter (never reset)
         for (int it = 0; it < my_tiles; ++it) {
-            const uint32_t jobbase = Cfg::RESIDENT ? 0u : (uint32_t)it * Cfg::JOBS;
-            const bool skip_w_wait = Cfg::RESIDENT && it > 0;
-            // ---- layer 2: job order (kb, nc)
-            if (me < Cfg::NI2) {
-                for (int kb = 0; kb < Cfg::KB1; ++kb) {
-                    const int nc = me;
-                    const uint32_t job = jobbase + kb * Cfg::NCH2 + nc;
+            if (Cfg::RESIDENT) { job = 0; w_ready = it > 0; }
+            // ---- layer 2
+            for (int nc = 0; nc < Cfg::NCH2; ++nc) {
+                for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
                     long long t0 = 0, t1 = 0, t2 = 0;
                     if (dbg) t0 = clock64();
-                    mbar_wait(&a1_ready[kb], it & 1);
+                    if (nc == 0) mbar_wait(&a_ready[kb], 0);
                     if (dbg) t1 = clock64();
-                    if (!skip_w_wait) mbar_wait(&w_full[st], ph);
+                    if (!w_ready) mbar_wait(&w_full[st], ph);
+                    w_ready = probe_next(job + 1);   // issued before the MMAs: its latency hides behind them
                     if (dbg) t2 = clock64();
                     tc_fence_after();
                     if (elect_one()) {
@@ -174,42 +166,38 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     if (dbg && dj < 1000) { long long *d = p.dbg_clocks + 4 * dj; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
                     ++dj;
                 }
-                if (elect_one()) mma_commit(acc2_full);
-                __syncwarp();
             }
-            // ---- layer 3: job order (chunk pair pp, kb, q); chunk 2*pp + q belongs to issuer q
-            if (me < Cfg::NQ) {
-                for (int pp = 0; pp < Cfg::NCH3 / Cfg::NQ; ++pp) {
-                    const uint32_t buf = (Cfg::NCH3 == 1) ? (uint32_t)(it & 1) : (uint32_t)me;
-                    const uint32_t u = (Cfg::NCH3 == 1) ? (uint32_t)(it >> 1) : use;
-                    mbar_wait(&acc3_empty[buf], (u & 1) ^ 1);
+            if (elect_one()) mma_commit(acc2_full);
+            __syncwarp();
+            // ---- layer 3
+            for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
+                const uint32_t buf = chunk & 1;
+                mbar_wait(&acc3_empty[buf], ((chunk >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
+                    const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
+                    long long t0 = 0, t1 = 0, t2 = 0;
+                    if (dbg) t0 = clock64();
+                    if (nc == 0) mbar_wait(&a_ready[kb], 1);
+                    if (dbg) t1 = clock64();
+                    if (!w_ready) mbar_wait(&w_full[st], ph);
+                    w_ready = probe_next(job + 1);
+                    if (dbg) t2 = clock64();
                     tc_fence_after();
-                    for (int kb = 0; kb < Cfg::KB2; ++kb) {
-                        const uint32_t job = jobbase + Cfg::JOBS2 + (pp * Cfg::KB2 + kb) * Cfg::NQ + me;
-                        const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
-                        long long t0 = 0, t1 = 0, t2 = 0;
-                        if (dbg) t0 = clock64();
-                        if (pp == 0) mbar_wait(&a2_ready[kb], it & 1);
-                        if (dbg) t1 = clock64();
-                        if (!skip_w_wait) mbar_wait(&w_full[st], ph);
-                        if (dbg) t2 = clock64();
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
-                            const uint64_t bd = bdesc0 + (uint64_t)(st * (TC_STAGE_BYTES >> 4));
+                    if (elect_one()) {
+                        const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
+                        const uint64_t bd = bdesc0 + (uint64_t)(st * (TC_STAGE_BYTES >> 4));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                mma_tf32(tmem_base + 256 + buf * 128, ad + 2 * k, bd + 2 * k, idesc3, (kb | k) != 0);
-                            if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
-                        }
-                        __syncwarp();
-                        if (dbg && dj < 1000) { long long *d = p.dbg_clocks + 4 * dj; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
-                        ++dj;
+                        for (int k = 0; k < 4; ++k)
+                            mma_tf32(tmem_base + 256 + buf * 128, ad + 2 * k, bd + 2 * k, idesc3, (kb | k) != 0);
+                        if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
                     }
-                    if (elect_one()) mma_commit(&acc3_full[buf]);
                     __syncwarp();
-                    ++use;
+                    if (dbg && dj < 1000) { long long *d = p.dbg_clocks + 4 * dj; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
+                    ++dj;
                 }
+                if (elect_one()) mma_commit(&acc3_full[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -271,7 +259,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a1_ready[kb]);
+                if (lane == 0) mbar_arrive(&a_ready[kb]);
             }
             // ---- epilogue 2: TMEM -> +bias, ReLU, TF32 -> A2 (same buffer; all layer-2 MMAs are done)
             if (dbgc) dc[2] = clock64();
@@ -294,7 +282,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a2_ready[kb]);
+                if (lane == 0) mbar_arrive(&a_ready[kb]);
             }
             // ---- epilogue 3: per 128-column chunk: TMEM -> registers (thread = row), transpose 16-column
             //      slabs through per-warp shared memory (thread = column), running max over the section's

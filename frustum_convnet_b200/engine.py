@@ -125,18 +125,7 @@ class FrustumEngine:
                 lay["w%dt" % j] = wf.t().contiguous()                           # (Ci,Co)
                 lay["b%d" % j] = sh.to(f32).contiguous()
                 if self.precision == 1 and j >= 2:
-                    # stage images in the kernel's job order (pointnet_tc.cu): layer 2 = (kb, n-chunk),
-                    # layer 3 = (chunk pair, kb, chunk parity) — the two MMA issuer warps take alternate chunks
-                    nch = min(c2, 128) if j == 2 else 128
-                    img = pack_sw128(wf, nch)
-                    n_chunks, kbs, blk = wf.shape[0] // nch, wf.shape[1] // 32, nch * 32
-                    img = img.view(n_chunks, kbs, blk)
-                    if j == 2:
-                        img = img.permute(1, 0, 2)
-                    else:
-                        nq = 2 if n_chunks >= 2 else 1
-                        img = img.view(n_chunks // nq, nq, kbs, blk).permute(0, 2, 1, 3)
-                    lay["w%d_tc" % j] = img.contiguous().view(-1)
+                    lay["w%d_tc" % j] = pack_sw128(wf, min(c2, 128) if j == 2 else 128)
             self.pn.append(lay)
         S, V = self.arch.num_scales, self.num_vec
         widths = (128, 256, 512, 512)[: S - 1]

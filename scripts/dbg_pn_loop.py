@@ -31,3 +31,14 @@ for s in [int(x) for x in sys.argv[1:]] or [0, 1, 2, 3]:
     except Exception as e:
         print("scale", s + 1, "FAILED", str(e)[:80], flush=True)
         break
+
+# timing of each scale kernel (hot, back to back)
+for s in range(4):
+    a = plan.pn_args[s]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(200):
+        _lib.call("fcn_pointnet_tiles", C.byref(a), st)
+    e1.record(); torch.cuda.synchronize()
+    print("scale", s + 1, "us per launch", e0.elapsed_time(e1) * 1000 / 200)
