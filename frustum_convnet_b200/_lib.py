@@ -81,7 +81,6 @@ SIGNATURES = {
     "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _P, _P, _P]),
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
     "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
-    "fcn_set_trap_buffer": (_I, [_P]),
 }
 
 _lib = None

@@ -366,8 +366,3 @@ int pointnet_tiles_tc(const fcn_pointnet_args &a, cudaStream_t stream) {
 
 }  // namespace fcn
 
-// Diagnostics (see include/frustum_b200.h): covers the mbarrier waits of the PointNet tensor-core kernel.
-extern "C" int fcn_set_trap_buffer(long long *host_mapped_device_ptr) {
-    FCN_CUDA(cudaMemcpyToSymbol(fcn::umma::g_trap_info, &host_mapped_device_ptr, sizeof(long long *)));
-    return FCN_OK;
-}

@@ -176,11 +176,6 @@ FCN_API int fcn_btc_to_bct(int B, int C, int T, int ld, const float *src, float 
 FCN_API int fcn_selftest_umma(int N, int K, const float *A, const void *w_img, float *D,
                               fcn_stream_t stream);
 
-/* Diagnostics: register a HOST-MAPPED (cudaHostAlloc mapped / pinned) buffer of >= 8 int64; a kernel
- * whose mbarrier wait times out records {magic, barrier smem address, parity, thread, block, barrier
- * state} there before trapping.  Pass NULL to disable. */
-FCN_API int fcn_set_trap_buffer(long long *host_mapped_device_ptr);
-
 #ifdef __cplusplus
 }
 #endif
