@@ -23,7 +23,6 @@ constexpr int TC_COMPUTE_WARPS = 8;
 constexpr int TC_THREADS = (TC_COMPUTE_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 16384;
 constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 32 rows x 32 columns per warp
-constexpr int TC_SLAB_ROWS = 32;
 constexpr int TC_SLAB_LD = TC_SLAB_COLS + 4;  // +4 floats: conflict-free float4 row writes / column reads
 
 __device__ __forceinline__ bool elect_one() {
@@ -44,14 +43,30 @@ struct TcCfg {
     static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
     static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 6 : JOBS);
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
+    // Small-channel scales are latency-bound per tile (tiny MMAs, long SIMT phases): run TWO CTAs per SM
+    // so that one CTA's epilogue overlaps the other's loads/MMAs.  That needs <= 113 KB of shared memory
+    // (16-row two-pass transposition slab) and <= 256 TMEM columns (single acc3 buffer: with one
+    // 128-column chunk per tile the second buffer never overlapped anything).
+    static constexpr int CTAS_PER_SM = (C1 <= 64) ? 2 : 1;
+    static constexpr int SLAB_ROWS = (CTAS_PER_SM == 2) ? 16 : 32;
+    static constexpr int TMEM_COLS = (CTAS_PER_SM == 2) ? 256 : 512;
+    static constexpr int ACC3_COL = (CTAS_PER_SM == 2) ? 128 : 256;
+    static constexpr int ACC3_BUFS = (CTAS_PER_SM == 2) ? 1 : 2;
+    static_assert(CTAS_PER_SM == 1 || (NCH3 == 1 && C2 <= 128), "2 CTAs/SM layout assumes one chunk per tile");
     static constexpr int OFF_W = A_BYTES;
-    static constexpr int OFF_RECS = OFF_W + NSTAGE * TC_STAGE_BYTES;
+    // resident weights are packed tightly (layer-2 stages are only N2 x 128 B), streamed stages use 16 KB slots
+    static constexpr int W_BYTES = RESIDENT ? (JOBS2 * N2 * 128 + JOBS3 * TC_STAGE_BYTES) : NSTAGE * TC_STAGE_BYTES;
+    __host__ __device__ static constexpr int stage_off(int st) {
+        return !RESIDENT ? st * TC_STAGE_BYTES
+                         : (st < JOBS2 ? st * N2 * 128 : JOBS2 * N2 * 128 + (st - JOBS2) * TC_STAGE_BYTES);
+    }
+    static constexpr int OFF_RECS = OFF_W + W_BYTES;
     static constexpr int OFF_W1 = OFF_RECS + 2 * TC_ROWS * 16;       // recs are double-buffered by tile parity
     static constexpr int OFF_B2 = OFF_W1 + C1 * 16;
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;                 // int sect[128]
     static constexpr int OFF_SLAB = OFF_SECT + 2 * TC_ROWS * 4;      // per-warp [32][TC_SLAB_LD] fp32
-    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * TC_SLAB_ROWS * TC_SLAB_LD * 4;
+    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * SLAB_ROWS * TC_SLAB_LD * 4;
     static constexpr int NBAR = 2 * NSTAGE + KBMAX + 1 + 4;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
@@ -59,10 +74,11 @@ struct TcCfg {
     static_assert(C2 <= 256, "acc2 occupies TMEM columns [0,256)");
     static_assert(C1 == C2, "a_ready phase bookkeeping assumes the same K-block count for A1 and A2");
     static_assert(BYTES <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
+    static_assert(CTAS_PER_SM == 1 || 2 * (BYTES + 1024) <= 233472, "two CTAs must fit in 228 KB per SM");
 };
 
 template <int C1, int C2, int C3>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, (TcCfg<C1, C2, C3>::CTAS_PER_SM))
 pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     using Cfg = TcCfg<C1, C2, C3>;
     extern __shared__ uint8_t smem_dyn[];
@@ -100,7 +116,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
         for (int i = 0; i < 2; ++i) { mbar_init(&acc3_full[i], 1); mbar_init(&acc3_empty[i], TC_COMPUTE_WARPS); }
         fence_barrier_init();
     }
-    if (warp == TC_COMPUTE_WARPS) tmem_alloc<512>(tmem_slot);
+    if (warp == TC_COMPUTE_WARPS) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -122,7 +138,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     const uint8_t *src = l2 ? (const uint8_t *)p.w2_tc + (size_t)j * (Cfg::N2 * 128)
                                             : (const uint8_t *)p.w3_tc + (size_t)(j - Cfg::JOBS2) * TC_STAGE_BYTES;
                     mbar_arrive_expect_tx(&w_full[st], bytes);
-                    bulk_g2s(sW + st * TC_STAGE_BYTES, src, bytes, &w_full[st]);
+                    bulk_g2s(sW + Cfg::stage_off(st), src, bytes, &w_full[st]);
                 }
             }
         }
@@ -156,7 +172,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
-                        const uint64_t bd = bdesc0 + (uint64_t)(st * (TC_STAGE_BYTES >> 4));
+                        const uint64_t bd = bdesc0 + (uint64_t)(Cfg::stage_off(st) >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             mma_tf32(tmem_base + nc * Cfg::N2, ad + 2 * k, bd + 2 * k, idesc2, (kb | k) != 0);
@@ -171,8 +187,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             __syncwarp();
             // ---- layer 3
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
-                const uint32_t buf = chunk & 1;
-                mbar_wait(&acc3_empty[buf], ((chunk >> 1) & 1) ^ 1);
+                const uint32_t buf = chunk % Cfg::ACC3_BUFS;
+                mbar_wait(&acc3_empty[buf], ((chunk / Cfg::ACC3_BUFS) & 1) ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = Cfg::RESIDENT ? 0 : (job / Cfg::NSTAGE) & 1;
@@ -186,10 +202,10 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
-                        const uint64_t bd = bdesc0 + (uint64_t)(st * (TC_STAGE_BYTES >> 4));
+                        const uint64_t bd = bdesc0 + (uint64_t)(Cfg::stage_off(st) >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_tf32(tmem_base + 256 + buf * 128, ad + 2 * k, bd + 2 * k, idesc3, (kb | k) != 0);
+                            mma_tf32(tmem_base + Cfg::ACC3_COL + buf * 128, ad + 2 * k, bd + 2 * k, idesc3, (kb | k) != 0);
                         if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
                     }
                     __syncwarp();
@@ -290,41 +306,53 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
             if (dbgc) dc[4] = clock64();
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
-            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (TC_SLAB_ROWS * TC_SLAB_LD);
+            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (Cfg::SLAB_ROWS * TC_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
-                const uint32_t buf = chunk & 1;
-                mbar_wait(&acc3_full[buf], (chunk >> 1) & 1);
+                const uint32_t buf = chunk % Cfg::ACC3_BUFS;
+                mbar_wait(&acc3_full[buf], (chunk / Cfg::ACC3_BUFS) & 1);
                 if (dbgc && nc < 5) dc[5 + 2 * nc] = clock64();
                 tc_fence_after();
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     const int col0 = h * 64 + half * 32;
                     uint32_t v[32];
-                    tmem_ld32(lane_taddr + 256 + buf * 128 + col0, v);
+                    tmem_ld32(lane_taddr + Cfg::ACC3_COL + buf * 128 + col0, v);
                     tmem_wait_ld();
                     // lane = column; the warp walks its 32 rows section by section (bounds are warp-uniform)
                     const int c = nc * Cfg::N3 + col0 + lane;
                     const float bias = b3s[c];
                     const float *col = slab + lane;
+                    constexpr int SR = Cfg::SLAB_ROWS, PASSES = 32 / SR;
+                    float run = -INFINITY;        // running max of the open section (carried across passes)
+#pragma unroll 1
+                    for (int pass = 0; pass < PASSES; ++pass) {
+                        if (PASSES == 1 || (lane / SR) == pass) {
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4)
-                        *(uint4 *)(slab + lane * TC_SLAB_LD + c4 * 4) =
-                            make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                    __syncwarp();
-                    unsigned em = endmask;
-                    int start = 0;
-                    while (em) {
-                        const int end = __ffs(em) - 1;
-                        em &= em - 1;
-                        float run = col[start * TC_SLAB_LD];
+                            for (int c4 = 0; c4 < 8; ++c4)
+                                *(uint4 *)(slab + (lane % SR) * TC_SLAB_LD + c4 * 4) =
+                                    make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                        }
+                        __syncwarp();
+                        unsigned em = (PASSES == 1) ? endmask : ((endmask >> (pass * SR)) & ((1u << SR) - 1u));
+                        int start = 0;
+                        while (em) {
+                            const int end = __ffs(em) - 1;
+                            em &= em - 1;
 #pragma unroll 4
-                        for (int r = start + 1; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
-                        const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
-                        if (o > 0.f)
-                            atomicMax(feat + (size_t)sect_s[q * 32 + end] * p.ld_feat + c, __float_as_int(o));
-                        start = end + 1;
+                            for (int r = start; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                            const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
+                            if (o > 0.f)
+                                atomicMax(feat + (size_t)sect_s[q * 32 + pass * SR + end] * p.ld_feat + c,
+                                          __float_as_int(o));
+                            run = -INFINITY;
+                            start = end + 1;
+                        }
+                        if (PASSES > 1) {   // open section continues in the next pass
+#pragma unroll 4
+                            for (int r = start; r < SR; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -337,7 +365,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     __syncthreads();
     if (warp == TC_COMPUTE_WARPS) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -346,7 +374,7 @@ static int launch_tc(const fcn_pointnet_args &a, cudaStream_t stream) {
     using Cfg = TcCfg<C1, C2, C3>;
     auto kern = pointnet_tc_kernel<C1, C2, C3>;
     FCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
-    int grid = sm_count();
+    int grid = sm_count() * Cfg::CTAS_PER_SM;
     if (grid > a.max_tiles) grid = a.max_tiles;
     if (grid < 1) return FCN_OK;
     FCN_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), (size_t)Cfg::BYTES, stream, a));
