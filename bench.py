@@ -251,18 +251,38 @@ def main():
         gather_bufs = [torch.empty((world,) + tuple(pl.out_flat.shape), dtype=torch.float32, device=dev)
                        for pl in plans]
 
-    def step_resident(i):
+    # N>1: the per-rank result blocks are all-gathered (NCCL over NVLink) on ONE communication stream,
+    # in step order on every rank (collectives of one communicator must not race on several streams);
+    # stream k waits for "its" gather before overwriting the output block in step i + nstream.
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_done = [None] * nstream
+
+    def gather(k):
+        ev = torch.cuda.Event()
+        ev.record(streams[k])
+        comm_stream.wait_event(ev)
+        with torch.cuda.stream(comm_stream):
+            dist.all_gather_into_tensor(gather_bufs[k], plans[k].out_flat)
+            done = torch.cuda.Event()
+            done.record(comm_stream)
+        gather_done[k] = done
+
+    def step_resident(i, comm=True):
         k = i % nstream
         with torch.cuda.stream(streams[k]):
+            if world > 1 and gather_done[k] is not None:
+                streams[k].wait_event(gather_done[k])
             out = model(dev_pool[i % npool])
-            if world > 1:
-                dist.all_gather_into_tensor(gather_bufs[k], plans[k].out_flat)
+        if world > 1 and comm:
+            gather(k)
         return out
 
     def join_streams():
         cur = torch.cuda.current_stream()
         for st in streams:
             cur.wait_stream(st)
+        if comm_stream is not None:
+            cur.wait_stream(comm_stream)
 
     def fork_streams():
         cur = torch.cuda.current_stream()
@@ -275,12 +295,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- timed region: inputs resident in HBM
-    t_pre = time.perf_counter()                      # untimed pre-warm: graph capture + clock ramp (~0.3 s)
-    j = 0
-    while time.perf_counter() - t_pre < 0.3 or j < 3 * nstream:
-        step_resident(j)
-        j += 1
-        if j % 64 == 0:
+    # untimed pre-warm: graph capture + clock ramp; a FIXED step count without collectives so that all
+    # ranks issue identical NCCL sequences afterwards
+    for j in range(512):
+        step_resident(j, comm=False)
+        if j % 64 == 63:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     for i in range(args.warmup):
@@ -311,7 +330,7 @@ def main():
     torch.cuda.synchronize()
     t_h = time.perf_counter()
     for i in range(32):
-        step_resident(i)
+        step_resident(i, comm=False)
     host_us = (time.perf_counter() - t_h) / 32 * 1e6
     torch.cuda.synchronize()
 
@@ -324,11 +343,13 @@ def main():
     def step_e2e(i):
         k = i % nstream
         with torch.cuda.stream(streams[k]):
+            if world > 1 and gather_done[k] is not None:
+                streams[k].wait_event(gather_done[k])
             plans[k].in_flat.copy_(host_pool[i % npool], non_blocking=True)    # H2D of this step's inputs
             model(in_views[k])                                                 # public API, zero-copy staging
             host_outs[k].copy_(plans[k].out_flat, non_blocking=True)           # D2H of the 6-tuple block
-            if world > 1:
-                dist.all_gather_into_tensor(gather_bufs[k], plans[k].out_flat)
+        if world > 1:
+            gather(k)
 
     for i in range(args.warmup):
         step_e2e(i)
