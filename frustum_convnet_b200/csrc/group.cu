@@ -90,7 +90,6 @@ constexpr int GE_THREADS = 512;
 
 __global__ void __launch_bounds__(GC_WARPS * 32)
 group_count_kernel(const __grid_constant__ GroupParams P) {
-    extern __shared__ float sz[];        // z row of this frustum
     const fcn_group_args &a = P.a;
     const int b = blockIdx.y;
     pdl_wait();
@@ -106,24 +105,48 @@ group_count_kernel(const __grid_constant__ GroupParams P) {
     }
     if (s >= a.num_scales) return;
     const int N = a.N, T = a.T[s], K = a.K[s];
-    const float *pz = a.pc + (size_t)b * 3 * N + 2 * (size_t)N;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) sz[i] = __ldg(pz + i);
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = chunk * GC_WARPS + warp;
+    const int t0 = chunk * GC_WARPS;
+    // this CTA owns the feature rows of its 32 sections: zero them and write the one-hot channels
+    // (det_base.py:145-157) here, where 600+ CTAs share the 11.5 MB instead of one CTA per (b, scale)
+    if (a.feat[s] != nullptr) {
+        const int ld = a.ld_feat[s], c3 = a.c3[s], V = a.num_vec;
+        const int nt = min(GC_WARPS, T - t0);
+        float4 *f4 = (float4 *)(a.feat[s] + ((size_t)b * T + t0) * ld);
+        const int n4 = nt * ld / 4;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) f4[i] = z4;
+        if (a.one_hot != nullptr && V > 0) {
+            __syncthreads();
+            float *fb = a.feat[s] + ((size_t)b * T + t0) * ld;
+            for (int i = threadIdx.x; i < nt * V; i += blockDim.x) {
+                const int t = i / V, v = i - t * V;
+                fb[(size_t)t * ld + c3 + v] = __ldg(a.one_hot + (size_t)b * V + v);
+            }
+        }
+    }
+    const int t = t0 + warp;
     if (t >= T) return;
+    // one warp per section; the z row is read straight from global memory (coalesced, L1-resident for the
+    // 32 warps of the CTA), four independent 32-point ballots in flight per step
+    const float *pz = a.pc + (size_t)b * 3 * N + 2 * (size_t)N;
     const float dis_z = a.dis_z[s];
     const float zc = __ldg(a.centers[s] + (size_t)b * 3 * T + 2 * (size_t)T + t);
     int *out = a.idx_scratch[s] + ((size_t)b * T + t) * K;
     const unsigned lt = (1u << lane) - 1u;
     int cnt = 0;
     for (int base = 0; base < N && cnt < K; base += 128) {
+        float zv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = base + j * 32 + lane;
+            zv[j] = k < N ? __ldg(pz + k) : 0.f;
+        }
         bool hit[4];
         unsigned m[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int k = base + j * 32 + lane;
-            hit[j] = (k < N) && depth_hit(zc, sz[k < N ? k : 0], dis_z);
+            hit[j] = (base + j * 32 + lane < N) && depth_hit(zc, zv[j], dis_z);
             m[j] = __ballot_sync(0xffffffffu, hit[j]);
         }
 #pragma unroll
@@ -193,22 +216,6 @@ group_emit_kernel(const __grid_constant__ GroupParams P) {
             const int row0 = i * a.tile_rows;
             if (s_tile_base + i < a.tile_cap[s])
                 tiles[s_tile_base + i] = make_int4(b, row0, min(a.tile_rows, total - row0), 0);
-        }
-    }
-    float *feat = a.feat[s];
-    if (feat != nullptr) {
-        const int ld = a.ld_feat[s], c3 = a.c3[s], V = a.num_vec;
-        float4 *f4 = (float4 *)(feat + (size_t)b * T * ld);
-        const int n4 = T * ld / 4;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) f4[i] = z4;
-        __syncthreads();
-        if (a.one_hot != nullptr) {
-            float *fb = feat + (size_t)b * T * ld;
-            for (int i = threadIdx.x; i < T * V; i += blockDim.x) {
-                const int t = i / V, v = i - t * V;
-                fb[(size_t)t * ld + c3 + v] = __ldg(a.one_hot + (size_t)b * V + v);
-            }
         }
     }
     // row records, one thread per row (independent gathers -> latency overlapped)
@@ -306,7 +313,7 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
     int nchunks = 0;
     for (int s = 0; s < a.num_scales; ++s) nchunks += ceil_div(a.T[s], GC_WARPS);
     dim3 gc(nchunks, a.B);
-    FCN_CUDA(launch_pdl(group_count_kernel, gc, dim3(GC_WARPS * 32), smem_c, (cudaStream_t)stream, P));
+    FCN_CUDA(launch_pdl(group_count_kernel, gc, dim3(GC_WARPS * 32), (size_t)0, (cudaStream_t)stream, P));
     dim3 ge(a.B, a.num_scales);
     FCN_CUDA(launch_pdl(group_emit_kernel, ge, dim3(GE_THREADS), smem_e, (cudaStream_t)stream, P));
     return FCN_OK;
