@@ -82,7 +82,36 @@ def run_case(name):
     print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def run_train_case(name="refine_car_train_b4"):
+    """Training branch (models/det_base.py:414-525): losses/metrics + a few gradients of the UNMODIFIED
+    reference in train mode (batch-statistics BN) on seeded inputs with labels."""
+    workload, B, dseed, wseed = "refine_car", 4, 206, 11
+    w = config.WORKLOADS[workload]
+    model, cfg = ref_import.load_reference_model(w["yaml"], w["num_vec"])
+    sd = synth.make_state_dict(w["arch"], w["num_vec"], cfg.DATA.DATASET_NAME, seed=wseed)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model.train()
+    data = synth.make_frustums(workload, B, seed=dseed, with_labels=True)
+    losses, metrics = model({k: torch.from_numpy(v) for k, v in data.items()})
+    losses["total_loss"].backward()
+    rec = {"input_checksum": np.array(checksum(data))}
+    for k, v in losses.items():
+        rec["loss_" + k] = v.detach().numpy()
+    for k in ("cls_acc", "head_acc", "size_acc"):
+        rec["metric_" + k] = metrics[k].detach().numpy()
+    for pn in ("cls_out.weight", "reg_out.bias", "feat_net.pointnet1.conv1.0.weight",
+               "conv_net.block4_merge.1.weight", "feat_net.pointnet4.conv3.1.bias"):
+        rec["grad_" + pn] = dict(model.named_parameters())[pn].grad.numpy()
+    rec["bn_running_mean"] = model.feat_net.pointnet1.conv1[1].running_mean.numpy()
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     assert ref_import.reference_available(), "needs /root/reference (authoring container only)"
     for n in (sys.argv[1:] or CASES):
-        run_case(n)
+        if n != "train":
+            run_case(n)
+    if not sys.argv[1:] or "train" in sys.argv[1:]:
+        run_train_case()
