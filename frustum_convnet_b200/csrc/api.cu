@@ -5,6 +5,7 @@
 namespace fcn {
 int pointnet_tiles_simt(const fcn_pointnet_args &a, cudaStream_t stream);
 int pointnet_tiles_tc(const fcn_pointnet_args &a, cudaStream_t stream);
+int pointnet_tiles_tc2(const fcn_pointnet_args &a, cudaStream_t stream);
 int conv_gemm_simt(const fcn_conv_args &a, cudaStream_t stream);
 int conv_gemm_tc(const fcn_conv_args &a, cudaStream_t stream);
 int conv_gemm_tma(const fcn_conv_args &a, cudaStream_t stream);
@@ -26,7 +27,8 @@ extern "C" int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t st
         return pointnet_tiles_simt(a, (cudaStream_t)stream);
     }
     if (a.precision == 1) return pointnet_tiles_tc(a, (cudaStream_t)stream);
-    return invalid(__func__, "precision must be 0 (fp32 SIMT) or 1 (TF32 tcgen05)");
+    if (a.precision == 2) return pointnet_tiles_tc2(a, (cudaStream_t)stream);
+    return invalid(__func__, "precision must be 0 (fp32 SIMT), 1 (TF32 tcgen05) or 2 (TF32 tcgen05, 2-CTA clusters)");
 }
 
 extern "C" int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream) {

@@ -95,6 +95,7 @@ class FrustumEngine:
         self.device = torch.device(device)
         self.precision = int(precision)
         self.use_tma = os.environ.get("FCN_CONV_TMA", "1") != "0"   # conv A operand via TMA tensor maps
+        self.pn_cluster = os.environ.get("FCN_PN_CLUSTER", "0") == "1"  # 2-CTA PointNet kernel for C1 >= 128
         self.tile_rows = 64 if self.precision == 0 else 128
         self.out_size = reg_out_size(dataset, self.num_bins)
         self.ld_logit = _round_up(2 + self.out_size, 64)
@@ -126,6 +127,8 @@ class FrustumEngine:
                 lay["b%d" % j] = sh.to(f32).contiguous()
                 if self.precision == 1 and j >= 2:
                     lay["w%d_tc" % j] = pack_sw128(wf, min(c2, 128) if j == 2 else 128)
+                    if self.pn_cluster and c1 >= 128:    # 2-CTA variant: one C2-wide / 256-wide tile per K block
+                        lay["w%d_tc2" % j] = pack_sw128(wf, c2 if j == 2 else 256)
             self.pn.append(lay)
         S, V = self.arch.num_scales, self.num_vec
         widths = (128, 256, 512, 512)[: S - 1]
@@ -332,6 +335,8 @@ class _Plan:
             a.w1t, a.b1, a.w2t, a.b2, a.w3t, a.b3 = (_ptr(w["w1t"]), _ptr(w["b1"]), _ptr(w["w2t"]),
                                                     _ptr(w["b2"]), _ptr(w["w3t"]), _ptr(w["b3"]))
             a.w2_tc, a.w3_tc = _ptr(w.get("w2_tc")), _ptr(w.get("w3_tc"))
+            if eng.precision == 1 and "w2_tc2" in w:
+                a.precision, a.w2_tc, a.w3_tc = 2, _ptr(w["w2_tc2"]), _ptr(w["w3_tc2"])
             a.out = _ptr(self.buf["feat%d" % (s + 1)])
             self.pn_args.append(a)
         self.conv_args = []

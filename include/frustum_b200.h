@@ -103,7 +103,9 @@ FCN_API int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream);
  *                zero-initialised, which fcn_group_rows does).
  *     unpooled : out = (B,C3,T,K) channel-first un-pooled masked tensor — the return value of
  *                PointNetModule.forward (det_base.py:103); rows must come from unique_rows=0.
- *     precision: 0 = fp32 SIMT, 1 = TF32 tensor cores (tcgen05) for the C1->C2->C3 layers.
+ *     precision: 0 = fp32 SIMT, 1 = TF32 tensor cores (tcgen05) for the C1->C2->C3 layers,
+ *                2 = same on 2-CTA clusters (cta_group::2, M = 256; scales with C1 >= 128; weight images
+ *                    packed with n-chunks C2 / 256).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     int C1, C2, C3, T, K, ld_feat, row_cap, tile_rows, unpooled, precision, B;
