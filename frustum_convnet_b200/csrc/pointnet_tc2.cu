@@ -186,6 +186,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             constexpr uint32_t idesc3 = make_idesc_tf32(256, Cfg::N3);
             const uint64_t adesc0 = make_desc_sw128(sA_addr), bdesc0 = make_desc_sw128(sW_addr);
             uint32_t job = 0;
+            const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && lane == 0;
             for (int it = 0; it < my_pairs; ++it) {
                 const uint32_t par = it & 1;
                 // ---- layer 2 -> region R0 (columns [0, C2))
@@ -193,8 +194,12 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 tc_fence_after();
                 for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = (job / Cfg::NSTAGE) & 1;
+                    long long t0 = 0, t1 = 0, t2 = 0;
+                    if (dbg) t0 = clock64();
                     mbar_wait(&a1_ready[kb], par);
+                    if (dbg) t1 = clock64();
                     mbar_wait(&w_full[st], ph);
+                    if (dbg) t2 = clock64();
                     tc_fence_after();
                     if (t2_elect_one()) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((T2_ROWS * 128) >> 4));
@@ -205,6 +210,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         mma_commit_2cta(&w_empty[st]);
                     }
                     __syncwarp();
+                    if (dbg && job < 1000) { long long *d = p.dbg_clocks + 4 * job; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
                 }
                 if (t2_elect_one()) mma_commit_2cta(acc2_full);
                 __syncwarp();
@@ -215,8 +221,12 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     const uint32_t dcol = nc == 0 ? 256u : 0u;
                     for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
                         const uint32_t st = job % Cfg::NSTAGE, ph = (job / Cfg::NSTAGE) & 1;
+                        long long t0 = 0, t1 = 0, t2 = 0;
+                        if (dbg) t0 = clock64();
                         if (nc == 0) mbar_wait(&a2_ready[kb], par);
+                        if (dbg) t1 = clock64();
                         mbar_wait(&w_full[st], ph);
+                        if (dbg) t2 = clock64();
                         tc_fence_after();
                         if (t2_elect_one()) {
                             const uint64_t ad = adesc0 + (uint64_t)(kb * ((T2_ROWS * 128) >> 4));
@@ -227,6 +237,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                             mma_commit_2cta(&w_empty[st]);
                         }
                         __syncwarp();
+                        if (dbg && job < 1000) { long long *d = p.dbg_clocks + 4 * job; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
                     }
                     if (t2_elect_one()) mma_commit_2cta(&acc3_full[nc]);
                     __syncwarp();
@@ -248,8 +259,11 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
         float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
         if (h == 0 && row < td_next.z)
             rec_next = ((const float4 *)p.rows + (size_t)td_next.x * p.row_cap + td_next.y)[row];
+        const bool dbgc = p.dbg_clocks != nullptr && blockIdx.x == 0 && tid == 0;
         for (int it = 0; it < my_pairs; ++it) {
             const uint32_t par = it & 1;
+            long long *dc = p.dbg_clocks + 4096 + 16 * it;
+            if (dbgc) dc[0] = clock64();
             const int4 td = td_next;
             const int b = td.x, nrows = td.z;
             float4 *recs = recs_all + (it & 1) * T2_ROWS;
@@ -291,7 +305,9 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 if (lane == 0) mbar_arrive_cluster(&a1_ready[kb], 0);
             }
             // ---- epilogue 2: TMEM R0 -> +bias, ReLU, TF32 -> A2 (same buffer)
+            if (dbgc) dc[2] = clock64();
             mbar_wait(acc2_full, par);
+            if (dbgc) dc[3] = clock64();
             tc_fence_after();
             for (int kb = h; kb < Cfg::KB2; kb += 2) {
                 uint32_t v[32];
@@ -312,11 +328,13 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 if (lane == 0) mbar_arrive_cluster(&a2_ready[kb], 0);
             }
             // ---- epilogue 3: 256-column chunks; warp (q,h) drains rows 32q.. x columns 128h..
+            if (dbgc) dc[4] = clock64();
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
             float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * T2_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc) {
                 const uint32_t dcol = nc == 0 ? 256u : 0u;
                 mbar_wait(&acc3_full[nc], par);
+                if (dbgc) dc[5 + 2 * nc] = clock64();
                 tc_fence_after();
 #pragma unroll 1
                 for (int part = 0; part < 4; ++part) {
@@ -349,6 +367,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
                 tc_fence_before();
                 __syncwarp();
+                if (dbgc) dc[6 + 2 * nc] = clock64();
                 // region drained: chunk 0 frees R1, chunk 1 frees R0 (both waited for by the leader's MMA warp)
                 if (lane == 0) mbar_arrive_cluster(&r_empty[nc == 0 ? 1 : 0], 0);
             }

@@ -34,8 +34,9 @@ tiles = t[4096:].reshape(-1, 16)
 tiles = tiles[tiles[:, 0] > 0]
 base = min(jobs[0, 0], tiles[0, 0])
 print("scale", scale + 1, "jobs", len(jobs), "tiles(CTA0)", len(tiles))
+print("precision", a.precision)
 print("MMA warp per job: start | wait_a  wait_w  issue")
-for j, r in enumerate(jobs[:80]):
+for j, r in enumerate(jobs[:56]):
     print("%3d %8d | %6d %6d %6d" % (j, r[0] - base, r[1] - r[0], r[2] - r[1], r[3] - r[2]))
 print("compute warp 0 per tile: start recs_ready | L1_done->acc2wait acc2_ready epi2_done | chunk: acc3_ready epi3_done ...")
 for r in tiles:
