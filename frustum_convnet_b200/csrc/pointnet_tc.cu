@@ -14,7 +14,6 @@
 // Replaces /root/reference/models/det_base.py:95-101 + the torch.max of :134-143 for one scale.
 #include "common.cuh"
 #include "umma.cuh"
-#include "pn_epilogue.cuh"
 
 namespace fcn {
 using namespace umma;
@@ -42,7 +41,7 @@ struct TcCfg {
     static constexpr int NCH3 = C3 / N3;
     static constexpr int A_BYTES = TC_ROWS * (C1 > C2 ? C1 : C2) * 4;
     static constexpr int JOBS2 = NCH2 * KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
-    static constexpr int NSTAGE = (C1 >= 256) ? 5 : (C1 >= 128 ? 8 : JOBS);
+    static constexpr int NSTAGE = (C1 >= 256) ? 3 : (C1 >= 128 ? 6 : JOBS);
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
     // Small-channel scales are latency-bound per tile (tiny MMAs, long SIMT phases): run TWO CTAs per SM
     // so that one CTA's epilogue overlaps the other's loads/MMAs.  That needs <= 113 KB of shared memory
@@ -67,7 +66,7 @@ struct TcCfg {
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;                 // int sect[128]
     static constexpr int OFF_SLAB = OFF_SECT + 2 * TC_ROWS * 4;      // per-warp [32][TC_SLAB_LD] fp32
-    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * 32 * 4;   // per-warp 128-byte flush row
+    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * SLAB_ROWS * TC_SLAB_LD * 4;
     static constexpr int NBAR = 2 * NSTAGE + KBMAX + 1 + 4;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
@@ -260,8 +259,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             const int nsect = __shfl_down_sync(0xffffffffu, sect, 1);
             const bool nvalid = (row + 1) < nrows;
             const unsigned endmask = __ballot_sync(0xffffffffu, valid && (lane == 31 || !nvalid || nsect != sect));
-            const int psect = __shfl_up_sync(0xffffffffu, sect, 1);
-            const int dist = segment_dist(valid, lane == 0 || psect != sect, lane);
 
             // ---- layer 1 (fp32 FMA) -> A1, K-blocks kb = h, h+2, ...
             for (int kb = h; kb < Cfg::KB1; kb += 2) {
@@ -309,7 +306,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
             if (dbgc) dc[4] = clock64();
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
-            float *srow = (float *)(smem + Cfg::OFF_SLAB) + warp * 32;
+            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (Cfg::SLAB_ROWS * TC_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
                 const uint32_t buf = chunk % Cfg::ACC3_BUFS;
                 mbar_wait(&acc3_full[buf], (chunk / Cfg::ACC3_BUFS) & 1);
@@ -321,8 +318,41 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     uint32_t v[32];
                     tmem_ld32(lane_taddr + Cfg::ACC3_COL + buf * 128 + col0, v);
                     tmem_wait_ld();
+                    // lane = column; the warp walks its 32 rows section by section (bounds are warp-uniform)
                     const int c = nc * Cfg::N3 + col0 + lane;
-                    segmax_flush32(v, dist, endmask, lane, srow, sect_s + q * 32, feat, p.ld_feat, c, b3s[c]);
+                    const float bias = b3s[c];
+                    const float *col = slab + lane;
+                    constexpr int SR = Cfg::SLAB_ROWS, PASSES = 32 / SR;
+                    float run = -INFINITY;        // running max of the open section (carried across passes)
+#pragma unroll 1
+                    for (int pass = 0; pass < PASSES; ++pass) {
+                        if (PASSES == 1 || (lane / SR) == pass) {
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4)
+                                *(uint4 *)(slab + (lane % SR) * TC_SLAB_LD + c4 * 4) =
+                                    make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                        }
+                        __syncwarp();
+                        unsigned em = (PASSES == 1) ? endmask : ((endmask >> (pass * SR)) & ((1u << SR) - 1u));
+                        int start = 0;
+                        while (em) {
+                            const int end = __ffs(em) - 1;
+                            em &= em - 1;
+#pragma unroll 4
+                            for (int r = start; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                            const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
+                            if (o > 0.f)
+                                atomicMax(feat + (size_t)sect_s[q * 32 + pass * SR + end] * p.ld_feat + c,
+                                          __float_as_int(o));
+                            run = -INFINITY;
+                            start = end + 1;
+                        }
+                        if (PASSES > 1) {   // open section continues in the next pass
+#pragma unroll 4
+                            for (int r = start; r < SR; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
+                        }
+                        __syncwarp();
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();

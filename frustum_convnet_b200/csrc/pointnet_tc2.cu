@@ -16,7 +16,6 @@
 // stage-empty / accumulator-full arrivals to the same barrier offsets in both CTAs.
 #include "common.cuh"
 #include "umma.cuh"
-#include "pn_epilogue.cuh"
 
 namespace fcn {
 using namespace umma;
@@ -25,7 +24,7 @@ constexpr int T2_ROWS = 128;
 constexpr int T2_COMPUTE_WARPS = 8;
 constexpr int T2_THREADS = (T2_COMPUTE_WARPS + 2) * 32;
 constexpr int T2_STAGE_BYTES = 16384;          // per CTA: half of a [256 x 128 B] weight tile
-constexpr int T2_SROW = 32;                  // floats of per-warp flush row (epilogue 3)
+constexpr int T2_SLAB_LD = 36;
 
 template <int C1, int C2, int C3>
 struct Tc2Cfg {
@@ -35,7 +34,7 @@ struct Tc2Cfg {
     static constexpr int JOBS2 = KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
     static constexpr int HALF2 = (N2 / 2) * 128, HALF3 = (N3 / 2) * 128;   // bytes per CTA per job
     static constexpr int A_BYTES = T2_ROWS * (C1 > C2 ? C1 : C2) * 4;
-    static constexpr int NSTAGE = (C1 >= 256) ? 5 : 8;
+    static constexpr int NSTAGE = (C1 >= 256) ? 3 : 6;
     static constexpr int OFF_W = A_BYTES;
     static constexpr int OFF_RECS = OFF_W + NSTAGE * T2_STAGE_BYTES;
     static constexpr int OFF_W1 = OFF_RECS + 2 * T2_ROWS * 16;
@@ -43,7 +42,7 @@ struct Tc2Cfg {
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;
     static constexpr int OFF_SLAB = OFF_SECT + 2 * T2_ROWS * 4;
-    static constexpr int OFF_BAR = OFF_SLAB + T2_COMPUTE_WARPS * T2_SROW * 4;
+    static constexpr int OFF_BAR = OFF_SLAB + T2_COMPUTE_WARPS * 32 * T2_SLAB_LD * 4;
     static constexpr int NBAR = 2 * NSTAGE + 2 * KBMAX + 1 + 2 + 2;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;
@@ -287,8 +286,6 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             const int nsect = __shfl_down_sync(0xffffffffu, sect, 1);
             const bool nvalid = (row + 1) < nrows;
             const unsigned endmask = __ballot_sync(0xffffffffu, valid && (lane == 31 || !nvalid || nsect != sect));
-            const int psect = __shfl_up_sync(0xffffffffu, sect, 1);
-            const int dist = segment_dist(valid, lane == 0 || psect != sect, lane);
 
             // ---- layer 1 (fp32 FMA) -> A1
             for (int kb = h; kb < Cfg::KB1; kb += 2) {
@@ -333,7 +330,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             // ---- epilogue 3: 256-column chunks; warp (q,h) drains rows 32q.. x columns 128h..
             if (dbgc) dc[4] = clock64();
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
-            float *srow = (float *)(smem + Cfg::OFF_SLAB) + warp * T2_SROW;
+            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * T2_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc) {
                 const uint32_t dcol = nc == 0 ? 256u : 0u;
                 mbar_wait(&acc3_full[nc], par);
@@ -346,7 +343,27 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     tmem_ld32(lane_taddr + dcol + col0, v);
                     tmem_wait_ld();
                     const int c = nc * Cfg::N3 + col0 + lane;
-                    segmax_flush32(v, dist, endmask, lane, srow, sect_s + q * 32, feat, p.ld_feat, c, b3s[c]);
+                    const float bias = b3s[c];
+                    const float *col = slab + lane;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *(uint4 *)(slab + lane * T2_SLAB_LD + c4 * 4) =
+                            make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                    __syncwarp();
+                    unsigned em = endmask;
+                    int start = 0;
+                    while (em) {
+                        const int end = __ffs(em) - 1;
+                        em &= em - 1;
+                        float run = col[start * T2_SLAB_LD];
+#pragma unroll 4
+                        for (int r = start + 1; r <= end; ++r) run = fmaxf(run, col[r * T2_SLAB_LD]);
+                        const float o = to_tf32(run + bias);
+                        if (o > 0.f)
+                            atomicMax(feat + (size_t)sect_s[q * 32 + end] * p.ld_feat + c, __float_as_int(o));
+                        start = end + 1;
+                    }
+                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();
