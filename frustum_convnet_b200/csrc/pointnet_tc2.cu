@@ -21,12 +21,10 @@ namespace fcn {
 using namespace umma;
 
 constexpr int T2_ROWS = 128;
-constexpr int T2_COMPUTE_WARPS = 16;           // 4 TMEM lane quadrants x 4 column/K-block groups
-constexpr int T2_NH = T2_COMPUTE_WARPS / 4;
+constexpr int T2_COMPUTE_WARPS = 8;
 constexpr int T2_THREADS = (T2_COMPUTE_WARPS + 2) * 32;
 constexpr int T2_STAGE_BYTES = 16384;          // per CTA: half of a [256 x 128 B] weight tile
 constexpr int T2_SLAB_LD = 36;
-constexpr int T2_SLAB_ROWS = 16;              // two-pass transposition slab (keeps 16 warps within the smem budget)
 
 template <int C1, int C2, int C3>
 struct Tc2Cfg {
@@ -44,7 +42,7 @@ struct Tc2Cfg {
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;
     static constexpr int OFF_SLAB = OFF_SECT + 2 * T2_ROWS * 4;
-    static constexpr int OFF_BAR = OFF_SLAB + T2_COMPUTE_WARPS * T2_SLAB_ROWS * T2_SLAB_LD * 4;
+    static constexpr int OFF_BAR = OFF_SLAB + T2_COMPUTE_WARPS * 32 * T2_SLAB_LD * 4;
     static constexpr int NBAR = 2 * NSTAGE + 2 * KBMAX + 1 + 2 + 2;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;
@@ -290,7 +288,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             const unsigned endmask = __ballot_sync(0xffffffffu, valid && (lane == 31 || !nvalid || nsect != sect));
 
             // ---- layer 1 (fp32 FMA) -> A1
-            for (int kb = h; kb < Cfg::KB1; kb += T2_NH) {
+            for (int kb = h; kb < Cfg::KB1; kb += 2) {
                 uint8_t *dst = sA + kb * (T2_ROWS * 128) + row_off;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
@@ -311,7 +309,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             mbar_wait(acc2_full, par);
             if (dbgc) dc[3] = clock64();
             tc_fence_after();
-            for (int kb = h; kb < Cfg::KB2; kb += T2_NH) {
+            for (int kb = h; kb < Cfg::KB2; kb += 2) {
                 uint32_t v[32];
                 tmem_ld32(lane_taddr + kb * 32, v);
                 tmem_wait_ld();
@@ -332,52 +330,40 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             // ---- epilogue 3: 256-column chunks; warp (q,h) drains rows 32q.. x columns 128h..
             if (dbgc) dc[4] = clock64();
             int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
-            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (T2_SLAB_ROWS * T2_SLAB_LD);
+            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * T2_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc) {
                 const uint32_t dcol = nc == 0 ? 256u : 0u;
                 mbar_wait(&acc3_full[nc], par);
                 if (dbgc) dc[5 + 2 * nc] = clock64();
                 tc_fence_after();
 #pragma unroll 1
-                for (int part = 0; part < 256 / (32 * T2_NH); ++part) {
-                    const int col0 = h * (256 / T2_NH) + part * 32;
+                for (int part = 0; part < 4; ++part) {
+                    const int col0 = h * 128 + part * 32;
                     uint32_t v[32];
                     tmem_ld32(lane_taddr + dcol + col0, v);
                     tmem_wait_ld();
                     const int c = nc * Cfg::N3 + col0 + lane;
                     const float bias = b3s[c];
                     const float *col = slab + lane;
-                    constexpr int SR = T2_SLAB_ROWS, PASSES = 32 / SR;
-                    float run = -INFINITY;        // running max of the open section (carried across passes)
-#pragma unroll 1
-                    for (int pass = 0; pass < PASSES; ++pass) {
-                        if (PASSES == 1 || (lane / SR) == pass) {
 #pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4)
-                                *(uint4 *)(slab + (lane % SR) * T2_SLAB_LD + c4 * 4) =
-                                    make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                        }
-                        __syncwarp();
-                        unsigned em = (PASSES == 1) ? endmask : ((endmask >> (pass * SR)) & ((1u << SR) - 1u));
-                        int start = 0;
-                        while (em) {
-                            const int end = __ffs(em) - 1;
-                            em &= em - 1;
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        *(uint4 *)(slab + lane * T2_SLAB_LD + c4 * 4) =
+                            make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+                    __syncwarp();
+                    unsigned em = endmask;
+                    int start = 0;
+                    while (em) {
+                        const int end = __ffs(em) - 1;
+                        em &= em - 1;
+                        float run = col[start * T2_SLAB_LD];
 #pragma unroll 4
-                            for (int r = start; r <= end; ++r) run = fmaxf(run, col[r * T2_SLAB_LD]);
-                            const float o = to_tf32(run + bias);
-                            if (o > 0.f)
-                                atomicMax(feat + (size_t)sect_s[q * 32 + pass * SR + end] * p.ld_feat + c,
-                                          __float_as_int(o));
-                            run = -INFINITY;
-                            start = end + 1;
-                        }
-                        if (PASSES > 1) {
-#pragma unroll 4
-                            for (int r = start; r < SR; ++r) run = fmaxf(run, col[r * T2_SLAB_LD]);
-                        }
-                        __syncwarp();
+                        for (int r = start + 1; r <= end; ++r) run = fmaxf(run, col[r * T2_SLAB_LD]);
+                        const float o = to_tf32(run + bias);
+                        if (o > 0.f)
+                            atomicMax(feat + (size_t)sect_s[q * 32 + end] * p.ld_feat + c, __float_as_int(o));
+                        start = end + 1;
                     }
+                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();

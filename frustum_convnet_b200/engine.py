@@ -95,7 +95,9 @@ class FrustumEngine:
         self.device = torch.device(device)
         self.precision = int(precision)
         self.use_tma = os.environ.get("FCN_CONV_TMA", "1") != "0"   # conv A operand via TMA tensor maps
-        self.pn_cluster = os.environ.get("FCN_PN_CLUSTER", "0") == "1"  # 2-CTA PointNet kernel for C1 >= 128
+        # 2-CTA (cta_group::2) PointNet kernel for the 256-channel scale(s): measured 57.5 -> 44.6 us on
+        # pointnet_s4; no gain at 128 channels (26.2 vs 27.0 us), so those stay on the 1-CTA kernel
+        self.pn_cluster = os.environ.get("FCN_PN_CLUSTER", "1") == "1"
         self.tile_rows = 64 if self.precision == 0 else 128
         self.out_size = reg_out_size(dataset, self.num_bins)
         self.ld_logit = _round_up(2 + self.out_size, 64)
@@ -127,7 +129,7 @@ class FrustumEngine:
                 lay["b%d" % j] = sh.to(f32).contiguous()
                 if self.precision == 1 and j >= 2:
                     lay["w%d_tc" % j] = pack_sw128(wf, min(c2, 128) if j == 2 else 128)
-                    if self.pn_cluster and c1 >= 128:    # 2-CTA variant: one C2-wide / 256-wide tile per K block
+                    if self.pn_cluster and c1 >= 256:    # 2-CTA variant: one C2-wide / 256-wide tile per K block
                         lay["w%d_tc2" % j] = pack_sw128(wf, c2 if j == 2 else 256)
             self.pn.append(lay)
         S, V = self.arch.num_scales, self.num_vec

@@ -35,8 +35,11 @@ def test_umma_selftest_matches_fp64_matmul(N, K):
     assert err < 1e-3 * max(1.0, float(ref.abs().max())), err
 
 
+@pytest.mark.parametrize("cluster", ["1", "0"])
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
-def test_pointnet_feat_tf32_matches_golden(name):
+def test_pointnet_feat_tf32_matches_golden(name, cluster, monkeypatch):
+    """cluster=1: 256-channel scale on the 2-CTA (cta_group::2) kernel; cluster=0: 1-CTA kernel everywhere."""
+    monkeypatch.setenv("FCN_PN_CLUSTER", cluster)
     g, data, sd, w, cfg = load_golden(name)
     m = build_model(w, sd, cfg)
     m.feat_net.precision = 1
