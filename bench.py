@@ -150,6 +150,14 @@ def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234):
     return sample_B / float(np.median(ts)), float(np.sum(ts)), n
 
 
+def workload_name(workload, B):
+    from frustum_convnet_b200 import config, synth
+    w = config.WORKLOADS[workload]
+    N = synth._PRESETS[workload]["N"]
+    return "%s cfgs/%s B=%d frustums/GPU x %d pts, T=%s, forward (eval)" % (
+        workload, w["yaml"], B, N, list(synth.section_counts(workload)))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -161,8 +169,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s det_sample B=%d x N pts (reference arm: %d-frustum sample per step)" % (
-            args.workload, args.batch, sample_B), "batch_per_gpu": args.batch},
+        "config": {"workload": workload_name(args.workload, args.batch),
+                   "batch_per_gpu": args.batch, "global_batch": args.batch, "parallelism": "dp1",
+                   "reference_sample": "%d frustums per step (bounded CPU sample of the same workload)" % sample_B},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
                          "sample": "%d steps x %d frustums, oracle port of models/det_base.py on torch CPU fp32"
                                    % (args.steps, sample_B)},
@@ -377,13 +386,19 @@ def main():
     peaks = load_peaks()
     algo = ALGO[args.workload]
     dom = max(kt["kernels"], key=lambda k: k["ms"])
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = tj.get(dom["name"], {}).get(args.workload, {}).get("bytes")
+    except Exception:
+        pass
     tf32_peak = peaks["bf16_tflops"] / 2.0   # kind::tf32 runs at half the bf16 rate; burst figure (kernel timed alone)
     roofline = {
         "bound": "tensor", "kernel": dom["name"], "achieved": dom["executed_tflops"], "peak": tf32_peak,
         "unit": "TFLOP/s", "frac": dom["executed_tflops"] / tf32_peak,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops/2 (%s)" % peaks["source"],
         "ms_per_launch": dom["ms"], "executed_gflop_per_launch": dom["executed_gflop"],
-        "nominal_gflop_per_launch": dom["nominal_gflop"], "traffic": None,
+        "nominal_gflop_per_launch": dom["nominal_gflop"], "traffic": traffic,
         "precision": "tf32-tcgen05" if args.precision == 1 else "fp32-simt",
     }
     hbm = {"achieved": value * algo["bytes"] / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -394,8 +409,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32" if args.precision == 1 else "f32", "data": "synthetic",
-        "config": {"workload": "%s cfgs/%s B=%d frustums/GPU x %d pts, T=%s, forward (eval)" % (
-            args.workload, w["yaml"], B, one["point_cloud"].shape[2], T),
+        "config": {"workload": workload_name(args.workload, B),
             "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
             "l2": "inputs cycle through a %d-batch pool (%.0f MB > 126 MB L2); weights/workspaces stay L2-resident"
                   % (npool, npool * step_in_bytes / 1e6),
