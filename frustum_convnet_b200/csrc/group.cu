@@ -149,6 +149,7 @@ group_count_kernel(const __grid_constant__ GroupParams P) {
             hit[j] = (base + j * 32 + lane < N) && depth_hit(zc, zv[j], dis_z);
             m[j] = __ballot_sync(0xffffffffu, hit[j]);
         }
+        if ((m[0] | m[1] | m[2] | m[3]) == 0u) continue;   // most 128-point steps miss a narrow section
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int pos = cnt + __popc(m[j] & lt);
