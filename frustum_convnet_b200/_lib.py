@@ -30,6 +30,7 @@ class GroupArgs(C.Structure):
         ("rows", C.c_void_p * MAX_SCALES), ("cnt", C.c_void_p * MAX_SCALES),
         ("feat", C.c_void_p * MAX_SCALES), ("tiles", C.c_void_p * MAX_SCALES),
         ("idx_scratch", C.c_void_p * MAX_SCALES),
+        ("feat_pitch", C.c_int * MAX_SCALES),
         ("ntiles", C.c_void_p),
     ]
 
@@ -44,13 +45,13 @@ class PointnetArgs(C.Structure):
         ("w1t", C.c_void_p), ("b1", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
         ("w3t", C.c_void_p), ("b3", C.c_void_p),
         ("w2_tc", C.c_void_p), ("w3_tc", C.c_void_p),
-        ("out", C.c_void_p), ("dbg_clocks", C.c_void_p),
+        ("out", C.c_void_p), ("dbg_clocks", C.c_void_p), ("feat_pitch", C.c_int),
     ]
 
 
 class ConvSeg(C.Structure):
     _fields_ = [("src", C.c_void_p), ("ld", C.c_int), ("C", C.c_int), ("T_src", C.c_int),
-                ("tap", C.c_int), ("stride", C.c_int)]
+                ("tap", C.c_int), ("stride", C.c_int), ("pitch", C.c_int)]
 
 
 class ConvArgs(C.Structure):
@@ -63,6 +64,7 @@ class ConvArgs(C.Structure):
         ("out", C.c_void_p),
         ("ld_out", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int), ("round_out", C.c_int),
         ("dbg_clocks", C.c_void_p), ("tmaps", C.c_void_p),
+        ("P_m", C.c_int), ("P_store", C.c_int),
     ]
 
 
@@ -76,9 +78,9 @@ SIGNATURES = {
     "fcn_group_rows": (_I, [C.POINTER(GroupArgs), _P]),
     "fcn_pointnet_tiles": (_I, [C.POINTER(PointnetArgs), _P]),
     "fcn_conv_gemm": (_I, [C.POINTER(ConvArgs), _P]),
-    "fcn_decode_eval": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "fcn_bct_to_btc": (_I, [_I, _I, _I, _I, _P, _P, _P]),
-    "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _P, _P, _P]),
+    "fcn_decode_eval": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fcn_bct_to_btc": (_I, [_I, _I, _I, _I, _I, _P, _P, _P]),
+    "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _I, _P, _P, _P]),
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
     "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
 }

@@ -15,7 +15,9 @@ using namespace fcn;
 
 extern "C" int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t stream) {
     FCN_REQUIRE(args != nullptr, "args is NULL");
-    const fcn_pointnet_args &a = *args;
+    fcn_pointnet_args a = *args;
+    if (a.feat_pitch == 0) a.feat_pitch = a.T;
+    FCN_REQUIRE(a.feat_pitch >= a.T, "feat_pitch must be >= T");
     FCN_REQUIRE(a.B >= 0 && a.T >= 1 && a.K >= 1, "bad B/T/K");
     if (a.B == 0 || a.max_tiles == 0) return FCN_OK;
     FCN_REQUIRE(a.rows && a.tiles && a.ntiles && a.out, "NULL pointer");
@@ -33,7 +35,12 @@ extern "C" int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t st
 
 extern "C" int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream) {
     FCN_REQUIRE(args != nullptr, "args is NULL");
-    const fcn_conv_args &a = *args;
+    fcn_conv_args a = *args;
+    if (a.P_m == 0) a.P_m = a.T_out;
+    if (a.P_store == 0) a.P_store = a.T_store;
+    for (int s = 0; s < a.n_seg && s < FCN_MAX_SEGS; ++s)
+        if (a.seg[s].pitch == 0) a.seg[s].pitch = a.seg[s].T_src;
+    FCN_REQUIRE(a.P_m >= a.T_out && a.P_store >= a.T_store, "pitches must cover the valid rows");
     FCN_REQUIRE(a.B >= 0 && a.T_out >= 0, "negative size");
     FCN_REQUIRE(a.n_seg >= 1 && a.n_seg <= FCN_MAX_SEGS, "n_seg out of range");
     FCN_REQUIRE(a.K_pad > 0 && a.K_pad % 32 == 0, "K_pad must be a positive multiple of 32");
@@ -45,6 +52,7 @@ extern "C" int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream) {
         FCN_REQUIRE(a.seg[s].src != nullptr, "NULL segment source");
         FCN_REQUIRE(a.seg[s].ld % 4 == 0 && a.seg[s].C >= 1 && a.seg[s].C <= a.seg[s].ld, "bad segment ld/C");
         FCN_REQUIRE(a.seg[s].stride >= 1 && a.seg[s].T_src >= 1, "bad segment stride/T");
+        FCN_REQUIRE(a.seg[s].pitch >= a.seg[s].T_src, "segment pitch must be >= T_src");
         k += ((a.seg[s].C + 31) / 32) * 32;
     }
     FCN_REQUIRE(k <= a.K_pad && a.K_pad - k < 64, "K_pad does not match the padded segments");

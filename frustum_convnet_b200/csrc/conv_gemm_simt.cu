@@ -25,7 +25,7 @@ conv_gemm_simt_kernel(const __grid_constant__ fcn_conv_args p) {
     __shared__ __align__(16) float sA[2][CG_TM * CG_LDA];
     __shared__ __align__(16) float sW[2][CG_KC * CG_TN];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    const int M = p.B * p.T_out;
+    const int M = p.B * p.P_m;
     const int m0 = blockIdx.x * CG_TM, n0 = blockIdx.y * CG_TN;
     const int nchunks = p.K_pad / CG_KC;
     pdl_wait();
@@ -38,10 +38,10 @@ conv_gemm_simt_kernel(const __grid_constant__ fcn_conv_args p) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int r = m0 + arow + h * 32;
-        arow_ok[h] = r < M;
-        const int rr = arow_ok[h] ? r : 0;
-        ab[h] = rr / p.T_out;
-        at[h] = rr - ab[h] * p.T_out;
+        const int rr = r < M ? r : 0;
+        ab[h] = rr / p.P_m;
+        at[h] = rr - ab[h] * p.P_m;
+        arow_ok[h] = r < M && at[h] < p.T_out;
     }
     const int wrow = tid >> 4, wcol = (tid & 15) * 4;
 
@@ -61,7 +61,7 @@ conv_gemm_simt_kernel(const __grid_constant__ fcn_conv_args p) {
         for (int h = 0; h < 2; ++h) {
             const int ts = at[h] * sg.stride + sg.tap;
             const bool ok = arow_ok[h] && ts >= 0 && ts < sg.T_src && c < sg.ld;
-            const float *src = ok ? sg.src + ((size_t)ab[h] * sg.T_src + ts) * sg.ld + c : sg.src;
+            const float *src = ok ? sg.src + ((size_t)ab[h] * sg.pitch + ts) * sg.ld + c : sg.src;
             cg_cp_async16(&sA[stage][(arow + h * 32) * CG_LDA + acol], src, ok);
         }
         const float *w = p.wt + (size_t)(kc * CG_KC) * p.n_cols + n0;
@@ -118,19 +118,19 @@ conv_gemm_simt_kernel(const __grid_constant__ fcn_conv_args p) {
     for (int r = 0; r < 4; ++r) {
         const int row = m0 + ty * 4 + r;
         if (row >= M) continue;
-        const int b = row / p.T_out, t = row - b * p.T_out;
+        const int b = row / p.P_m, t = row - b * p.P_m;
         const int tt = t * p.up + jj;
-        if (tt >= p.T_store) continue;
+        if (t >= p.T_out || tt >= p.T_store) continue;
         float4 o = make_float4(acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w);
         if (p.relu) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
-        *(float4 *)(p.out + ((size_t)b * p.T_store + tt) * p.ld_out + p.c_off + co) = o;
+        *(float4 *)(p.out + ((size_t)b * p.P_store + tt) * p.ld_out + p.c_off + co) = o;
     }
 }
 
 int conv_gemm_simt(const fcn_conv_args &a, cudaStream_t stream) {
-    const int M = a.B * a.T_out;
+    const int M = a.B * a.P_m;
     if (M == 0) return FCN_OK;
     dim3 grid(ceil_div(M, CG_TM), a.n_cols / CG_TN);
     FCN_CUDA(launch_pdl(conv_gemm_simt_kernel, grid, dim3(CG_THREADS), (size_t)0, stream, a));

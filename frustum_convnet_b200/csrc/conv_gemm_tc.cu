@@ -56,7 +56,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
     uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int M = p.B * p.T_out;
+    const int M = p.B * p.P_m;
     const int m0 = blockIdx.x * GT_ROWS, n_tile = blockIdx.y;
     const int NS = p.K_pad / 64;                 // pipeline stages of 64 K elements
 
@@ -132,9 +132,10 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
         for (int j = 0; j < 8; ++j) {
             const int lr = warp * 32 + j * 4 + (lane >> 3);
             const int gr = m0 + lr;
-            const bool okr = gr < M;
-            gb[j] = okr ? gr / p.T_out : 0;
-            gt[j] = okr ? gr - gb[j] * p.T_out : 0;
+            const int grr = gr < M ? gr : 0;
+            gb[j] = grr / p.P_m;
+            gt[j] = grr - gb[j] * p.P_m;
+            const bool okr = gr < M && gt[j] < p.T_out;
             gok |= (okr ? 1u : 0u) << j;
             gdst[j] = smem_u32(sA) + (uint32_t)((lr >> 3) * 1024 + (lr & 7) * 128 + ((chunk ^ (lr & 7)) << 4));
         }
@@ -149,7 +150,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
                 const int ts = gt[j] * sg.stride + sg.tap;
                 const bool ok = ((gok >> j) & 1u) && ts >= 0 && ts < sg.T_src;
                 okm |= (ok ? 1u : 0u) << j;
-                rp[j] = sg.src + ((size_t)gb[j] * sg.T_src + (ok ? ts : 0)) * sg.ld + chunk * 4;
+                rp[j] = sg.src + ((size_t)gb[j] * sg.pitch + (ok ? ts : 0)) * sg.ld + chunk * 4;
             }
             const int nkb = (sg.C + 31) >> 5;
             for (int kbi = 0; kbi < nkb; ++kbi, ++kbg) {
@@ -187,9 +188,9 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
         // ---- epilogue: TMEM -> +bias (+ReLU, TF32 rounding) -> position-major global store
         const int row = warp * 32 + lane;
         const int r = m0 + row;
-        const bool row_ok = r < M;
-        const int rb = row_ok ? r / p.T_out : 0;
-        const int rt = row_ok ? r - rb * p.T_out : 0;
+        const int rb = r < M ? r / p.P_m : 0;
+        const int rt = r < M ? r - rb * p.P_m : 0;
+        const bool row_ok = r < M && rt < p.T_out;
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -203,7 +204,7 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
             const int jj = n / p.Cout, co = n - jj * p.Cout;
             const int tt = rt * p.up + jj;
             if (tt >= p.T_store) continue;
-            float *out = p.out + ((size_t)rb * p.T_store + tt) * p.ld_out + p.c_off + co;
+            float *out = p.out + ((size_t)rb * p.P_store + tt) * p.ld_out + p.c_off + co;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 bb = __ldg((const float4 *)(p.bias + n + c * 4));
@@ -230,7 +231,7 @@ static int launch_gt(const fcn_conv_args &a, cudaStream_t stream) {
     using Cfg = GtCfg<NT>;
     auto kern = conv_gemm_tc_kernel<NT>;
     FCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
-    const int M = a.B * a.T_out;
+    const int M = a.B * a.P_m;
     dim3 grid(ceil_div(M, GT_ROWS), a.n_cols / NT);
     FCN_CUDA(launch_pdl(kern, grid, dim3(GT_THREADS), (size_t)Cfg::BYTES, stream, a));
     return FCN_OK;

@@ -67,8 +67,10 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvTmaParams P) {
     uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tpf = (p.T_out + GM_ROWS - 1) / GM_ROWS;          // tiles per frustum
-    const int b = blockIdx.x / tpf, t0 = (blockIdx.x - b * tpf) * GM_ROWS;
+    // GEMM rows are the flattened (frustum, position) rows of the PADDED activation maps: row r = b*P_m + t.
+    // The pad rows between frustums are zero, so kernel taps / the stride-2 sampling need no per-frustum
+    // handling (pitch of every source == stride * P_m) and every 128-row tile is fully used.
+    const int r0 = blockIdx.x * GM_ROWS;
     const int n_tile = blockIdx.y;
     const int NS = p.K_pad / 64;
 
@@ -102,10 +104,10 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvTmaParams P) {
                     const uint32_t dst = smem_u32(sA) + st * Cfg::A_STAGE + a * Cfg::A_ATOM;
                     if (seg < p.n_seg) {
                         const fcn_conv_seg &sg = p.seg[seg];
-                        tma_load_3d(dst, &P.maps[seg], kbi * 32, t0 * sg.stride + sg.tap, b, &full[st]);
+                        tma_load_3d(dst, &P.maps[seg], kbi * 32, r0 * sg.stride + sg.tap, 0, &full[st]);
                         if (++kbi >= ((sg.C + 31) >> 5)) { kbi = 0; ++seg; }
                     } else {   // K padding block: a box fully outside the channel range -> zeros
-                        tma_load_3d(dst, &P.maps[0], 1 << 20, 0, b, &full[st]);
+                        tma_load_3d(dst, &P.maps[0], 1 << 20, 0, 0, &full[st]);
                     }
                 }
                 bulk_g2s(sW + st * Cfg::W_STAGE, wsrc + (size_t)s * Cfg::W_STAGE, Cfg::W_STAGE, &full[st]);
@@ -138,8 +140,9 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvTmaParams P) {
     } else {
         // ================= epilogue: TMEM -> +bias (+ReLU, TF32 rounding) -> position-major store =========
         const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int rt = t0 + q * 32 + lane;            // output position of this thread's row
-        const bool row_ok = rt < p.T_out;
+        const int r = r0 + q * 32 + lane;             // flattened GEMM row of this thread
+        const int b = r / p.P_m, rt = r - b * p.P_m;  // (frustum, position)
+        const bool row_ok = r < p.B * p.P_m && rt < p.T_out;
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -153,7 +156,7 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvTmaParams P) {
             const int jj = n / p.Cout, co = n - jj * p.Cout;
             const int tt = rt * p.up + jj;
             if (tt >= p.T_store) continue;
-            float *out = p.out + ((size_t)b * p.T_store + tt) * p.ld_out + p.c_off + co;
+            float *out = p.out + ((size_t)b * p.P_store + tt) * p.ld_out + p.c_off + co;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 bb = __ldg((const float4 *)(p.bias + n + c * 4));
@@ -199,7 +202,7 @@ static int launch_gm(const ConvTmaParams &P, cudaStream_t stream) {
     auto kern = conv_gemm_tma_kernel<NT>;
     FCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
     const fcn_conv_args &a = P.a;
-    dim3 grid(a.B * ceil_div(a.T_out, GM_ROWS), a.n_cols / NT);
+    dim3 grid(ceil_div(a.B * a.P_m, GM_ROWS), a.n_cols / NT);
     FCN_CUDA(launch_pdl(kern, grid, dim3(GM_THREADS), (size_t)Cfg::BYTES, stream, P));
     return FCN_OK;
 }
@@ -210,6 +213,11 @@ int conv_gemm_tma(const fcn_conv_args &a, cudaStream_t stream) {
     FCN_REQUIRE(a.tmaps != nullptr, "NULL tensor maps (fcn_encode_activation_map)");
     FCN_REQUIRE(a.Cout % 32 == 0, "tensor-core variant needs Cout % 32 == 0");
     FCN_REQUIRE(a.K_pad % 64 == 0, "tensor-core variant needs K_pad % 64 == 0");
+    for (int s = 0; s < a.n_seg; ++s) {
+        FCN_REQUIRE(a.seg[s].pitch == a.seg[s].stride * a.P_m, "TMA variant: source pitch must equal stride * P_m");
+        FCN_REQUIRE(a.seg[s].tap == 0 || a.seg[s].pitch > a.seg[s].T_src,
+                    "TMA variant: kernel taps need zero pad rows between frustums (pitch > T_src)");
+    }
     if (a.B * a.T_out == 0) return FCN_OK;
     ConvTmaParams P;
     memcpy(P.maps, a.tmaps, sizeof(CUtensorMap) * a.n_seg);

@@ -112,13 +112,14 @@ group_count_kernel(const __grid_constant__ GroupParams P) {
     if (a.feat[s] != nullptr) {
         const int ld = a.ld_feat[s], c3 = a.c3[s], V = a.num_vec;
         const int nt = min(GC_WARPS, T - t0);
-        float4 *f4 = (float4 *)(a.feat[s] + ((size_t)b * T + t0) * ld);
+        const int fp = a.feat_pitch[s] > 0 ? a.feat_pitch[s] : T;
+        float4 *f4 = (float4 *)(a.feat[s] + ((size_t)b * fp + t0) * ld);
         const int n4 = nt * ld / 4;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i = threadIdx.x; i < n4; i += blockDim.x) f4[i] = z4;
         if (a.one_hot != nullptr && V > 0) {
             __syncthreads();
-            float *fb = a.feat[s] + ((size_t)b * T + t0) * ld;
+            float *fb = a.feat[s] + ((size_t)b * fp + t0) * ld;
             for (int i = threadIdx.x; i < nt * V; i += blockDim.x) {
                 const int t = i / V, v = i - t * V;
                 fb[(size_t)t * ld + c3 + v] = __ldg(a.one_hot + (size_t)b * V + v);

@@ -197,7 +197,7 @@ pointnet_simt_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     }
                 }
                 __syncthreads();
-                int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
+                int *feat = (int *)(p.out + (size_t)b * p.feat_pitch * p.ld_feat);
                 for (int i = tid; i < nrank * PT_NC; i += PT_THREADS) {
                     const int rr = i >> 6, col = i & 63;
                     const int v = smax[rr * (PT_NC + 1) + col];

@@ -305,7 +305,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             //      rows, then +bias, ReLU and a coalesced integer atomicMax into the feature map
             //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
             if (dbgc) dc[4] = clock64();
-            int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
+            int *feat = (int *)(p.out + (size_t)b * p.feat_pitch * p.ld_feat);
             float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (Cfg::SLAB_ROWS * TC_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
                 const uint32_t buf = chunk % Cfg::ACC3_BUFS;

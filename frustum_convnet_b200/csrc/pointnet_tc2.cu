@@ -329,7 +329,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             }
             // ---- epilogue 3: 256-column chunks; warp (q,h) drains rows 32q.. x columns 128h..
             if (dbgc) dc[4] = clock64();
-            int *feat = (int *)(p.out + (size_t)b * p.T * p.ld_feat);
+            int *feat = (int *)(p.out + (size_t)b * p.feat_pitch * p.ld_feat);
             float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * T2_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc) {
                 const uint32_t dcol = nc == 0 ? 256u : 0u;

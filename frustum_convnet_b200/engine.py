@@ -262,6 +262,16 @@ class _Plan:
         f32 = torch.float32
         K = arch.nsample
         tr = eng.tile_rows
+        # Row pitch of every position-major map: P_S = T_S + 1, P_i = 2 * P_{i+1}.  Each frustum is followed
+        # by >= 1 zero pad row (never written), so the FCN GEMMs can run over the FLATTENED rows of the
+        # whole batch (full 128-row tiles): k=3 taps read a zero row instead of the neighbouring frustum,
+        # and stride-2 layers map flat row r to input rows 2r-1..2r+1 because the pitch halves per level.
+        P = [0] * S
+        P[S - 1] = T[S - 1] + 1
+        for i in range(S - 2, -1, -1):
+            P[i] = 2 * P[i + 1]
+            assert P[i] >= T[i] + 1
+        self.P = P
         self.buf: Dict[str, torch.Tensor] = {}
         self.rows, self.cnt, self.tiles, self.max_tiles, self.idx32 = [], [], [], [], []
         for s in range(S):
@@ -272,15 +282,19 @@ class _Plan:
             mt = B * ((cap + tr - 1) // tr)
             self.max_tiles.append(mt)
             self.tiles.append(torch.empty((max(mt, 1), 4), dtype=torch.int32, device=dev))
-            self.buf["feat%d" % (s + 1)] = torch.empty((B, T[s], eng.ld_feat[s]), dtype=f32, device=dev)
+            self.buf["feat%d" % (s + 1)] = torch.zeros((B, P[s], eng.ld_feat[s]), dtype=f32, device=dev)
         self.ntiles = torch.zeros(_lib.MAX_SCALES, dtype=torch.int32, device=dev)
         widths = (128, 256, 512, 512)[: S - 1]
-        self.buf["x1"] = torch.empty((B, T[0], arch.block1_out), dtype=f32, device=dev)
+        self.buf["x1"] = torch.zeros((B, P[0], arch.block1_out), dtype=f32, device=dev)
+        self.valid_T = {"x1": T[0], "cat": T[1], "logits": T[1]}
         for i in range(2, S + 1):
             for nm in ("a", "b", "m"):
-                self.buf["%s%d" % (nm, i)] = torch.empty((B, T[i - 1], widths[i - 2]), dtype=f32, device=dev)
-        self.buf["cat"] = torch.empty((B, T[1], 256 * (S - 1)), dtype=f32, device=dev)
-        self.buf["logits"] = torch.empty((B, T[1], eng.ld_logit), dtype=f32, device=dev)
+                self.buf["%s%d" % (nm, i)] = torch.zeros((B, P[i - 1], widths[i - 2]), dtype=f32, device=dev)
+                self.valid_T["%s%d" % (nm, i)] = T[i - 1]
+        for s in range(S):
+            self.valid_T["feat%d" % (s + 1)] = T[s]
+        self.buf["cat"] = torch.zeros((B, P[1], 256 * (S - 1)), dtype=f32, device=dev)
+        self.buf["logits"] = torch.zeros((B, P[1], eng.ld_logit), dtype=f32, device=dev)
         T2 = T[1]
         # the six outputs of det_base.py:411 are views into one flat block (single all-gather / D2H)
         widths_out = (2, 3, 1, 3, eng.num_bins, eng.num_size)
@@ -321,6 +335,7 @@ class _Plan:
             g.rows[s], g.cnt[s] = _ptr(self.rows[s]), _ptr(self.cnt[s])
             g.feat[s], g.tiles[s] = _ptr(self.buf["feat%d" % (s + 1)]), _ptr(self.tiles[s])
             g.idx_scratch[s] = _ptr(self.idx32[s])
+            g.feat_pitch[s] = self.P[s]
         g.ntiles = _ptr(self.ntiles)
         self.group_args = g
         self.pn_args = []
@@ -340,21 +355,25 @@ class _Plan:
             if eng.precision == 1 and "w2_tc2" in w:
                 a.precision, a.w2_tc, a.w3_tc = 2, _ptr(w["w2_tc2"]), _ptr(w["w3_tc2"])
             a.out = _ptr(self.buf["feat%d" % (s + 1)])
+            a.feat_pitch = self.P[s]
             self.pn_args.append(a)
         self.conv_args = []
         self._tmaps = []
         for L in eng.layers:
             a = _lib.ConvArgs()
             out = self.buf[L.out]
-            first_src = self.buf[L.segs[0][0]]
+            src0 = L.segs[0][0]
             stride = L.segs[0][3]
             a.B = self.B
-            a.T_out = first_src.shape[1] if stride == 1 else (first_src.shape[1] + 1) // 2
+            T_in, P_in = self.valid_T[src0], self.buf[src0].shape[1]
+            a.T_out = T_in if stride == 1 else (T_in + 1) // 2
+            a.P_m = P_in // stride
             a.n_seg = len(L.segs)
             for j, (src, c, tap, st) in enumerate(L.segs):
                 t = self.buf[src]
                 a.seg[j].src, a.seg[j].ld, a.seg[j].C = _ptr(t), t.shape[2], c
-                a.seg[j].T_src, a.seg[j].tap, a.seg[j].stride = t.shape[1], tap, st
+                a.seg[j].T_src, a.seg[j].tap, a.seg[j].stride = self.valid_T[src], tap, st
+                a.seg[j].pitch = t.shape[1]
             a.K_pad, a.n_cols, a.Cout, a.up, a.relu = L.K_pad, L.n_cols, L.Cout, L.up, L.relu
             a.precision, a.w_tc = 0, None
             if eng.precision == 1 and L.Cout % 32 == 0:
@@ -368,7 +387,7 @@ class _Plan:
                     for j, (src, c, tap, st) in enumerate(L.segs):
                         t = self.buf[src]
                         _lib.call("fcn_encode_activation_map", C.addressof(maps) + 128 * j, _ptr(t),
-                                  self.B, t.shape[1], t.shape[2], st)
+                                  1, self.B * t.shape[1], t.shape[2], st)   # flattened padded rows
                     self._tmaps.append(maps)
                     a.tmaps = C.addressof(maps)
                     a.precision = 3 if nt == 128 else 4
@@ -376,7 +395,8 @@ class _Plan:
                     a.precision = 1 if nt == 128 else 2
             a.round_out = 1 if (eng.precision == 1 and L.name != "heads") else 0
             a.wt, a.bias = _ptr(L.wt), _ptr(L.bias)
-            a.out, a.ld_out, a.T_store, a.c_off = _ptr(out), out.shape[2], out.shape[1], L.c_off
+            a.out, a.ld_out, a.T_store, a.c_off = _ptr(out), out.shape[2], self.valid_T[L.out], L.c_off
+            a.P_store = out.shape[1]
             self.conv_args.append(a)
 
     # ---- launch sequences (all asynchronous on the current stream)
@@ -454,7 +474,7 @@ class _Plan:
     def _launch_decode(self, center_ref2):
         eng = self.eng
         o = self.out
-        _lib.call("fcn_decode_eval", self.B, self.T[1], eng.ld_logit, eng.num_bins, eng.num_size,
+        _lib.call("fcn_decode_eval", self.B, self.T[1], self.P[1], eng.ld_logit, eng.num_bins, eng.num_size,
                   _ptr(self.buf["logits"]), _ptr(center_ref2), _ptr(eng.mean_size), _ptr(o[0]), _ptr(o[1]),
                   _ptr(o[2]), _ptr(o[3]), _ptr(o[4]), _ptr(o[5]), _stream())
 
@@ -568,7 +588,7 @@ class _Plan:
             for s in range(eng.arch.num_scales):
                 c = eng.c3[s] + eng.num_vec
                 o = torch.empty((self.B, c, self.T[s]), dtype=torch.float32, device=eng.device)
-                _lib.call("fcn_btc_to_bct", self.B, c, self.T[s], eng.ld_feat[s],
+                _lib.call("fcn_btc_to_bct", self.B, c, self.T[s], self.P[s], eng.ld_feat[s],
                           _ptr(self.buf["feat%d" % (s + 1)]), _ptr(o), _stream())
                 outs.append(o)
         return tuple(outs)
@@ -580,7 +600,7 @@ class _Plan:
                 c = eng.c3[s] + eng.num_vec
                 assert f.is_cuda and f.dtype == torch.float32 and f.is_contiguous()
                 assert tuple(f.shape) == (self.B, c, self.T[s]), "feat%d has shape %s" % (s + 1, tuple(f.shape))
-                _lib.call("fcn_bct_to_btc", self.B, c, self.T[s], eng.ld_feat[s], _ptr(f),
+                _lib.call("fcn_bct_to_btc", self.B, c, self.T[s], self.P[s], eng.ld_feat[s], _ptr(f),
                           _ptr(self.buf["feat%d" % (s + 1)]), _stream())
             st = _stream()
             for a, L in zip(self.conv_args, eng.layers):
@@ -588,8 +608,9 @@ class _Plan:
                     continue
                 _lib.call("fcn_conv_gemm", C.byref(a), st)
             cat = self.buf["cat"]
-            o = torch.empty((self.B, cat.shape[2], cat.shape[1]), dtype=torch.float32, device=eng.device)
-            _lib.call("fcn_btc_to_bct", self.B, cat.shape[2], cat.shape[1], cat.shape[2], _ptr(cat), _ptr(o), st)
+            T2 = self.T[1]
+            o = torch.empty((self.B, cat.shape[2], T2), dtype=torch.float32, device=eng.device)
+            _lib.call("fcn_btc_to_bct", self.B, cat.shape[2], T2, cat.shape[1], cat.shape[2], _ptr(cat), _ptr(o), st)
         return o
 
     def time_kernels(self, dev_pool, iters=20):
@@ -660,7 +681,7 @@ class _Plan:
 
     def logits(self):
         """(B*T2, 2) class scores and (B*T2, out) regression rows of the last run (views)."""
-        lg = self.buf["logits"].view(-1, self.eng.ld_logit)
+        lg = self.buf["logits"][:, :self.T[1], :].reshape(-1, self.eng.ld_logit)
         return lg[:, 0:2], lg[:, 2:2 + self.eng.out_size]
 
 

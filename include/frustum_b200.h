@@ -89,6 +89,7 @@ typedef struct {
     float *feat[FCN_MAX_SCALES];            /* (B,T_s,ld_feat) or NULL */
     void *tiles[FCN_MAX_SCALES];            /* int4[tile_cap] */
     int32_t *idx_scratch[FCN_MAX_SCALES];   /* (B,T_s,K_s) int32: first min(hits,K) point indices */
+    int feat_pitch[FCN_MAX_SCALES];         /* rows per frustum of feat[s] (>= T_s; 0 means T_s) */
     int32_t *ntiles;                        /* int32[FCN_MAX_SCALES] */
 } fcn_group_args;
 FCN_API int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream);
@@ -117,6 +118,7 @@ typedef struct {
     const void *w2_tc, *w3_tc;  /* tensor-core packed images (precision=1), else NULL */
     float *out;
     long long *dbg_clocks;  /* optional (NULL): CTA 0 dumps pipeline timestamps (diagnostics) */
+    int feat_pitch;         /* rows per frustum of the pooled feature map (>= T; 0 means T) */
 } fcn_pointnet_args;
 FCN_API int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t stream);
 
@@ -135,6 +137,9 @@ FCN_API int fcn_pointnet_tiles(const fcn_pointnet_args *args, fcn_stream_t strea
 typedef struct {
     const float *src;
     int ld, C, T_src, tap, stride;
+    int pitch;   /* rows per frustum of src (>= T_src; 0 means T_src).  Padded maps (pitch > T_src, pad rows
+                    kept zero) let the GEMM run over the flattened (frustum, position) rows: the kernel
+                    taps then read a zero pad row instead of the neighbouring frustum. */
 } fcn_conv_seg;
 typedef struct {
     int B, T_out, n_seg;
@@ -147,12 +152,16 @@ typedef struct {
     int round_out;   /* 1: round outputs to TF32 (cvt.rna) because a tensor-core GEMM consumes them */
     long long *dbg_clocks; /* optional (NULL): CTA (0,0) dumps per-K-block pipeline timestamps, 8 per K block */
     const void *tmaps;     /* HOST pointer to n_seg 128-byte tensor maps (precision 3|4), see below */
+    int P_m;               /* pitch of the GEMM row space: row r = b*P_m + t, valid iff t < T_out (0: T_out) */
+    int P_store;           /* rows per frustum of `out` (>= T_store; 0 means T_store) */
 } fcn_conv_args;
 FCN_API int fcn_conv_gemm(const fcn_conv_args *args, fcn_stream_t stream);
 
 /* TMA descriptor of a position-major activation map (B,T,ld) fp32 for the fully TMA-fed conv GEMM
  * (precision 3 = N tile 128, 4 = N tile 64): 3-D tensor (channel, position, frustum), box
  * 32 x 128 x 1 with 128-byte swizzle, position step t_stride (1, or 2 for the stride-2 convs).
+ * The kernel addresses the GEMM rows as ONE flattened sequence, so encode the map with B = 1 and
+ * T = (number of frustums) x pitch of the padded activation map.
  * Writes 128 bytes to HOST memory; pass an array of them (one per segment) in fcn_conv_args.tmaps. */
 FCN_API int fcn_encode_activation_map(void *out_map_128B, const float *base, int B, int T, int ld,
                                       int t_stride);
@@ -160,17 +169,19 @@ FCN_API int fcn_encode_activation_map(void *out_map_128B, const float *base, int
 /* ------------------------------------------------------------------------------------------
  * (5) Eval decode of the head logits.  Replaces models/det_base.py:376-411 and
  *     models/box_transform.py:5-12,28-41.
- *     logits: (B*T, ld) rows = [cls0, cls1, center(3), heading scores(NH), heading res(NH),
+ *     logits: (B, pitch >= T, ld) rows = [cls0, cls1, center(3), heading scores(NH), heading res(NH),
  *     size scores(NS), size res(NS*3)];  center_ref: (B,3,T) channel-first;  mean_size (NS,3).
  * ------------------------------------------------------------------------------------------ */
-FCN_API int fcn_decode_eval(int B, int T, int ld, int num_heading_bin, int num_size, const float *logits,
+FCN_API int fcn_decode_eval(int B, int T, int pitch, int ld, int num_heading_bin, int num_size, const float *logits,
                     const float *center_ref, const float *mean_size, float *cls_probs,
                     float *center, float *heading, float *size, float *heading_probs,
                     float *size_probs, fcn_stream_t stream);
 
-/* Layout helpers for the channel-first module APIs: (B,C,T) <-> (B,T,ld). */
-FCN_API int fcn_bct_to_btc(int B, int C, int T, int ld, const float *src, float *dst, fcn_stream_t stream);
-FCN_API int fcn_btc_to_bct(int B, int C, int T, int ld, const float *src, float *dst, fcn_stream_t stream);
+/* Layout helpers for the channel-first module APIs: (B,C,T) <-> (B,pitch >= T,ld) position-major. */
+FCN_API int fcn_bct_to_btc(int B, int C, int T, int pitch, int ld, const float *src, float *dst,
+                           fcn_stream_t stream);
+FCN_API int fcn_btc_to_bct(int B, int C, int T, int pitch, int ld, const float *src, float *dst,
+                           fcn_stream_t stream);
 
 /* Self-test of the tcgen05/TMEM/bulk-copy building blocks: D (128,N) = A (128,K) * W^T with W given
  * as the pre-swizzled stage image of the host packer (engine.pack_sw128).  N in {64,128},

@@ -36,7 +36,7 @@ def test_argument_validation_without_gpu():
     assert b"nsample" in lib.fcn_last_error()
     assert lib.fcn_query_depth_point_b3n(0, 4, 4, 0.5, 4, None, None, None, None, None) == 0  # empty batch
     assert lib.fcn_group_rows(None, None) == -1
-    assert lib.fcn_decode_eval(1, 1, 8, 12, 3, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.fcn_decode_eval(1, 1, 1, 8, 12, 3, None, None, None, None, None, None, None, None, None, None) == -1
     with pytest.raises(RuntimeError):
         _lib.call("fcn_conv_gemm", None, None)
 

@@ -188,7 +188,7 @@ def test_decode_kernel_on_reference_logits(name):
     ref2 = torch.from_numpy(data["center_ref2"]).to(dev())
     f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev())
     o = (f(B, T, 2), f(B, T, 3), f(B, T), f(B, T, 3), f(B, T, eng.num_bins), f(B, T, eng.num_size))
-    _lib.call("fcn_decode_eval", B, T, eng.ld_logit, eng.num_bins, eng.num_size, lg.data_ptr(),
+    _lib.call("fcn_decode_eval", B, T, T, eng.ld_logit, eng.num_bins, eng.num_size, lg.data_ptr(),
               ref2.data_ptr(), eng.mean_size.data_ptr(), *[t.data_ptr() for t in o],
               torch.cuda.current_stream().cuda_stream)
     for j in range(6):
