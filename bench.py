@@ -193,7 +193,7 @@ def main():
                     help="1: TF32 tensor cores (tcgen05) — the arithmetic cuDNN uses by default; 0: fp32 FMA")
     ap.add_argument("--pool-mb", type=float, default=160.0, help="distinct input pool size (> L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "4")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "8")),
                     help="forwards in flight: steps are issued round-robin on this many CUDA streams")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
