@@ -247,6 +247,180 @@ group_emit_kernel(const __grid_constant__ GroupParams P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused grouping, single launch (used whenever the hit bitmasks of one (frustum, scale) fit in shared
+// memory): instead of letting every section scan all N points (N*T predicate evaluations per scale —
+// group_count_kernel is issue-bound), every POINT marks the sections it falls into in a T x N bit matrix:
+//   phase 1  thread per point: when the section centres are sorted (the data providers emit them in
+//            ascending depth) a binary search finds the first centre >= z and the exact fp32 predicate is
+//            walked left/right from there (the hit set is contiguous for sorted centres because the rounded
+//            difference is monotone); unsorted centres fall back to testing all T sections.  Hits are
+//            atomicOr'ed into the section's row of the bit matrix.
+//   phase 2  warp per section: popcount prefix over the row's words gives every hit its rank in ascending
+//            point order — exactly the order of the reference's serial scan (cu:42-63); cnt = min(hits, K).
+//   then     block scan of cnt -> row offsets, tile table, zero-filled feature rows + one-hot, row records.
+// Same outputs (rows, tiles, cnt, feat) as group_count_kernel + group_emit_kernel, bit-exact.
+constexpr int GB_THREADS = 1024;
+
+__global__ void __launch_bounds__(GB_THREADS)
+group_bitmask_kernel(const __grid_constant__ GroupParams P) {
+    extern __shared__ unsigned sm_u[];
+    const fcn_group_args &a = P.a;
+    const int b = blockIdx.x, s = blockIdx.y;
+    const int N = a.N, T = a.T[s], K = a.K[s];
+    const int W = (N + 31) >> 5;                       // words per section row
+    unsigned *bm = sm_u;                               // T * W
+    float *zc = (float *)(bm + (size_t)T * W);         // T
+    int *scnt = (int *)(zc + T), *sstart = scnt + T;   // T, T
+    __shared__ int s_warp_tot[GB_THREADS / 32];
+    __shared__ int s_carry, s_total, s_tile_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    pdl_wait();
+    pdl_launch_dependents();
+    const float dis_z = a.dis_z[s];
+    const float *pz = a.pc + (size_t)b * 3 * N + 2 * (size_t)N;
+    const float *cen = a.centers[s] + (size_t)b * 3 * T;
+    for (int i = tid; i < T * W; i += blockDim.x) bm[i] = 0u;
+    for (int i = tid; i < T; i += blockDim.x) zc[i] = __ldg(cen + 2 * T + i);
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    int sorted = 1;
+    for (int i = tid; i + 1 < T; i += blockDim.x) sorted &= (zc[i + 1] >= zc[i]) ? 1 : 0;   // NaN -> unsorted
+    sorted = __syncthreads_and(sorted);
+
+    // ---- phase 1: points -> bit matrix
+    for (int k = tid; k < N; k += blockDim.x) {
+        const float z = __ldg(pz + k);
+        const unsigned bit = 1u << (k & 31);
+        unsigned *col = bm + (k >> 5);
+        if (sorted) {
+            int lo = 0, hi = T;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (zc[mid] < z) lo = mid + 1; else hi = mid;
+            }
+            for (int t = lo - 1; t >= 0 && depth_hit(zc[t], z, dis_z); --t) atomicOr(col + (size_t)t * W, bit);
+            for (int t = lo; t < T && depth_hit(zc[t], z, dis_z); ++t) atomicOr(col + (size_t)t * W, bit);
+        } else {
+            for (int t = 0; t < T; ++t)
+                if (depth_hit(zc[t], z, dis_z)) atomicOr(col + (size_t)t * W, bit);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2a: hits per section
+    for (int t = warp; t < T; t += nwarp) {
+        int c = 0;
+        for (int w = lane; w < W; w += 32) c += __popc(bm[(size_t)t * W + w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) scnt[t] = min(c, K);
+    }
+    __syncthreads();
+    // ---- exclusive scan of rows-per-section
+    const bool uniq = a.unique_rows != 0;
+    for (int base = 0; base < T; base += blockDim.x) {
+        const int t = base + tid;
+        int v = 0;
+        if (t < T) v = uniq ? scnt[t] : K;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_warp_tot[w];
+        const int carry = s_carry;
+        if (t < T) sstart[t] = carry + woff + incl - v;
+        __syncthreads();
+        if (tid == blockDim.x - 1) s_carry = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int total = s_carry;
+        s_total = total;
+        const int nt = ceil_div(total, a.tile_rows);
+        s_tile_base = nt > 0 ? atomicAdd(a.ntiles + s, nt) : 0;
+    }
+    __syncthreads();
+    const int total = s_total;
+    {
+        int4 *tiles = (int4 *)a.tiles[s];
+        const int nt = ceil_div(total, a.tile_rows);
+        for (int i = tid; i < nt; i += blockDim.x) {
+            const int row0 = i * a.tile_rows;
+            if (s_tile_base + i < a.tile_cap[s])
+                tiles[s_tile_base + i] = make_int4(b, row0, min(a.tile_rows, total - row0), 0);
+        }
+        int *gcnt = a.cnt[s] + (size_t)b * T;
+        for (int i = tid; i < T; i += blockDim.x) gcnt[i] = scnt[i];
+    }
+    if (a.feat[s] != nullptr) {   // zero-filled feature rows + one-hot channels (det_base.py:145-157)
+        const int ld = a.ld_feat[s], c3 = a.c3[s], V = a.num_vec;
+        const int fp = a.feat_pitch[s] > 0 ? a.feat_pitch[s] : T;
+        float *fb = a.feat[s] + (size_t)b * fp * ld;
+        float4 *f4 = (float4 *)fb;
+        const int n4 = T * ld / 4;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < n4; i += blockDim.x) f4[i] = z4;
+        if (a.one_hot != nullptr && V > 0) {
+            __syncthreads();
+            for (int i = tid; i < T * V; i += blockDim.x) {
+                const int t = i / V, v = i - t * V;
+                fb[(size_t)t * ld + c3 + v] = __ldg(a.one_hot + (size_t)b * V + v);
+            }
+        }
+    }
+    // ---- phase 2b: row records in ascending point order (rank = popcount prefix inside the section's row)
+    const float *px = a.pc + (size_t)b * 3 * N, *py = px + N;
+    float4 *rows = (float4 *)a.rows[s] + (size_t)b * a.row_cap[s];
+    for (int t = warp; t < T; t += nwarp) {
+        const int c = scnt[t];
+        if (c == 0 && uniq) continue;
+        const float cx = __ldg(cen + t), cy = __ldg(cen + T + t), czz = zc[t];
+        float4 *out = rows + sstart[t];
+        const int tag = c > 0 ? t : (t | 0x80000000);
+        int done = 0, first = 0x7fffffff;
+        for (int wb = 0; wb < W && done < K; wb += 32) {
+            const int w = wb + lane;
+            unsigned word = w < W ? bm[(size_t)t * W + w] : 0u;
+            const int n = __popc(word);
+            int incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            int pos = done + incl - n;
+            if (word && first == 0x7fffffff) first = w * 32 + __ffs(word) - 1;
+            while (word && pos < K) {
+                const int k = w * 32 + __ffs(word) - 1;
+                word &= word - 1;
+                out[pos++] = make_float4(__fsub_rn(__ldg(px + k), cx), __fsub_rn(__ldg(py + k), cy),
+                                         __fsub_rn(__ldg(pz + k), czz), __int_as_float(tag));
+            }
+            done += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (!uniq) {   // reference back-fill (cu:55-59): slots >= cnt repeat the first hit (point 0 if none)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            const int k = c > 0 ? first : 0;
+            const float4 r = make_float4(__fsub_rn(__ldg(px + k), cx), __fsub_rn(__ldg(py + k), cy),
+                                         __fsub_rn(__ldg(pz + k), czz), __int_as_float(tag));
+            for (int l = c + lane; l < K; l += 32) out[l] = r;
+        }
+    }
+}
+
+// ntiles reset for the single-launch path (a tiny grid in front of group_bitmask_kernel)
+__global__ void group_reset_kernel(int32_t *ntiles) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x < FCN_MAX_SCALES) ntiles[threadIdx.x] = 0;
+}
+
 }  // namespace fcn
 
 using namespace fcn;
@@ -302,14 +476,27 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
         FCN_REQUIRE(a.feat[s] == nullptr || a.ld_feat[s] >= a.c3[s] + a.num_vec, "ld_feat too small");
         maxT = a.T[s] > maxT ? a.T[s] : maxT;
     }
-    for (int s = 0; s < a.num_scales; ++s) FCN_REQUIRE(a.idx_scratch[s] != nullptr, "NULL idx_scratch");
-    const size_t smem_c = sizeof(float) * (size_t)a.N, smem_e = sizeof(int) * 5 * (size_t)maxT;
-    FCN_REQUIRE(smem_c <= 200 * 1024 && smem_e <= 200 * 1024, "N/T too large for the shared-memory staging");
-    FCN_REQUIRE(a.B <= 65535 && a.num_scales <= 65535, "grid too large");
     GroupParams P;
     P.a = a;
-    if (smem_c > 48 * 1024)
-        FCN_CUDA(cudaFuncSetAttribute(group_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    // single-launch bit-matrix path when T x N bits (+ 3T words) of the largest scale fit in shared memory
+    size_t smem_b = 0;
+    for (int s = 0; s < a.num_scales; ++s) {
+        const size_t need = sizeof(unsigned) * ((size_t)a.T[s] * ((a.N + 31) / 32) + 3 * (size_t)a.T[s]);
+        smem_b = need > smem_b ? need : smem_b;
+    }
+    static const bool force_scan = getenv("FCN_GROUP_SCAN") != nullptr;   // diagnostics / A-B testing
+    FCN_REQUIRE(a.B <= 65535 && a.num_scales <= 65535, "grid too large");
+    if (smem_b <= 200 * 1024 && !force_scan) {
+        if (smem_b > 48 * 1024)
+            FCN_CUDA(cudaFuncSetAttribute(group_bitmask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        FCN_CUDA(launch_pdl(group_reset_kernel, dim3(1), dim3(32), (size_t)0, (cudaStream_t)stream, a.ntiles));
+        FCN_CUDA(launch_pdl(group_bitmask_kernel, dim3(a.B, a.num_scales), dim3(GB_THREADS), smem_b,
+                            (cudaStream_t)stream, P));
+        return FCN_OK;
+    }
+    for (int s = 0; s < a.num_scales; ++s) FCN_REQUIRE(a.idx_scratch[s] != nullptr, "NULL idx_scratch");
+    const size_t smem_e = sizeof(int) * 5 * (size_t)maxT;
+    FCN_REQUIRE(smem_e <= 200 * 1024, "T too large for the shared-memory staging");
     if (smem_e > 48 * 1024)
         FCN_CUDA(cudaFuncSetAttribute(group_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     int nchunks = 0;
