@@ -373,16 +373,15 @@ group_bitmask_kernel(const __grid_constant__ GroupParams P) {
             }
         }
     }
-    // ---- phase 2b: row records in ascending point order (rank = popcount prefix inside the section's row)
-    const float *px = a.pc + (size_t)b * 3 * N, *py = px + N;
-    float4 *rows = (float4 *)a.rows[s] + (size_t)b * a.row_cap[s];
+    // ---- phase 2b: rank every hit (popcount prefix inside the section's row = ascending point order) and park
+    //      its point index in shared memory; then one thread per row gathers and writes the record
+    //      (independent loads, coalesced 16-byte stores)
+    int *rowk = sstart + T;                            // row_cap ints
     for (int t = warp; t < T; t += nwarp) {
         const int c = scnt[t];
-        if (c == 0 && uniq) continue;
-        const float cx = __ldg(cen + t), cy = __ldg(cen + T + t), czz = zc[t];
-        float4 *out = rows + sstart[t];
-        const int tag = c > 0 ? t : (t | 0x80000000);
-        int done = 0, first = 0x7fffffff;
+        if (c == 0) continue;
+        int *dst = rowk + sstart[t];
+        int done = 0;
         for (int wb = 0; wb < W && done < K; wb += 32) {
             const int w = wb + lane;
             unsigned word = w < W ? bm[(size_t)t * W + w] : 0u;
@@ -394,23 +393,37 @@ group_bitmask_kernel(const __grid_constant__ GroupParams P) {
                 if (lane >= o) incl += u;
             }
             int pos = done + incl - n;
-            if (word && first == 0x7fffffff) first = w * 32 + __ffs(word) - 1;
             while (word && pos < K) {
-                const int k = w * 32 + __ffs(word) - 1;
+                dst[pos++] = w * 32 + __ffs(word) - 1;
                 word &= word - 1;
-                out[pos++] = make_float4(__fsub_rn(__ldg(px + k), cx), __fsub_rn(__ldg(py + k), cy),
-                                         __fsub_rn(__ldg(pz + k), czz), __int_as_float(tag));
             }
             done += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (!uniq) {   // reference back-fill (cu:55-59): slots >= cnt repeat the first hit (point 0 if none)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-            const int k = c > 0 ? first : 0;
-            const float4 r = make_float4(__fsub_rn(__ldg(px + k), cx), __fsub_rn(__ldg(py + k), cy),
-                                         __fsub_rn(__ldg(pz + k), czz), __int_as_float(tag));
-            for (int l = c + lane; l < K; l += 32) out[l] = r;
+    }
+    __syncthreads();
+    const float *px = a.pc + (size_t)b * 3 * N, *py = px + N;
+    float4 *rows = (float4 *)a.rows[s] + (size_t)b * a.row_cap[s];
+    const int nrows_total = uniq ? total : T * K;
+    for (int i = tid; i < nrows_total; i += blockDim.x) {
+        int t, l;
+        if (uniq) {   // last t with sstart[t] <= i (empty sections share the offset of their successor)
+            int lo = 0, hi = T - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (sstart[mid] <= i) lo = mid; else hi = mid - 1;
+            }
+            t = lo;
+            l = i - sstart[t];
+        } else {
+            t = i / K;
+            l = i - t * K;
         }
+        const int c = scnt[t];
+        // reference back-fill (cu:55-59): slots >= cnt repeat the first hit; masked sections gather point 0
+        const int k = c > 0 ? rowk[sstart[t] + (l < c ? l : 0)] : 0;
+        const int tag = c > 0 ? t : (t | 0x80000000);
+        rows[i] = make_float4(__fsub_rn(__ldg(px + k), __ldg(cen + t)), __fsub_rn(__ldg(py + k), __ldg(cen + T + t)),
+                              __fsub_rn(__ldg(pz + k), zc[t]), __int_as_float(tag));
     }
 }
 
@@ -481,7 +494,8 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
     // single-launch bit-matrix path when T x N bits (+ 3T words) of the largest scale fit in shared memory
     size_t smem_b = 0;
     for (int s = 0; s < a.num_scales; ++s) {
-        const size_t need = sizeof(unsigned) * ((size_t)a.T[s] * ((a.N + 31) / 32) + 3 * (size_t)a.T[s]);
+        const size_t need = sizeof(unsigned) * ((size_t)a.T[s] * ((a.N + 31) / 32) + 3 * (size_t)a.T[s] +
+                                                (size_t)a.T[s] * a.K[s]);
         smem_b = need > smem_b ? need : smem_b;
     }
     static const bool force_scan = getenv("FCN_GROUP_SCAN") != nullptr;   // diagnostics / A-B testing
