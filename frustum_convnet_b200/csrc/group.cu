@@ -498,7 +498,7 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
                                                 (size_t)a.T[s] * a.K[s]);
         smem_b = need > smem_b ? need : smem_b;
     }
-    static const bool force_scan = getenv("FCN_GROUP_SCAN") != nullptr;   // diagnostics / A-B testing
+    const bool force_scan = getenv("FCN_GROUP_SCAN") != nullptr;   // A-B testing of the two grouping paths
     FCN_REQUIRE(a.B <= 65535 && a.num_scales <= 65535, "grid too large");
     if (smem_b <= 200 * 1024 && !force_scan) {
         if (smem_b > 48 * 1024)

@@ -96,3 +96,19 @@ def test_tf32_full_size_car_b32_vs_fp32_path():
     o2 = m1(d)
     for a, b in zip(o1, o2):
         assert torch.equal(a, b)      # deterministic (max-combine is order independent)
+
+
+@pytest.mark.parametrize("variant", ["FCN_CONV_TMA=0", "FCN_GROUP_SCAN=1", "FCN_PN_CLUSTER=0"])
+@pytest.mark.parametrize("name", ["car_full_b1", "sunrgbd_full_b2"])
+def test_alternative_kernel_variants_match_golden(name, variant, monkeypatch):
+    """The documented alternative kernels (cp.async-gather conv GEMM, section-scan grouping, 1-CTA PointNet
+    at 256 channels) stay parity-green: whole forward vs the reference fixture."""
+    k, v = variant.split("=")
+    monkeypatch.setenv(k, v)
+    g, data, sd, w, cfg = load_golden(name)
+    m = build_model(w, sd, cfg)
+    m.precision = 1
+    out = m(cuda_data(data))
+    close(out[0], g["out0"], tol=1e-2, what=variant + " cls_probs")
+    close(out[1], g["out1"], tol=1e-2, what=variant + " center")
+    close(out[4], g["out4"], tol=1e-2, what=variant + " heading_probs")
