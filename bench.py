@@ -53,7 +53,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle sampling during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle-reason sampling during the timed regions (B200_PROFILING.md clocks line).
+
+    The timed regions last tens of milliseconds, far less than an `nvidia-smi` start-up, so the sampling is done
+    in-process through NVML (`pynvml`, 1 ms period); `nvidia-smi -lms` is only the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -61,8 +64,29 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.sm, self.reasons, self.smax = [], set(), None
+        self.nvml, self.h, self.run = None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ent = vis.split(",")[gpu_index].strip()
+                phys = int(ent) if ent.isdigit() else None
+            self.h = (pynvml.nvmlDeviceGetHandleByIndex(phys) if phys is not None
+                      else pynvml.nvmlDeviceGetHandleByUUID(ent))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def start(self):
+        if self.nvml is not None:
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
@@ -73,11 +97,34 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        flags = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in flags:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.run = False
+            self.t.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax,
+                    "sm_min_mhz": float(min(self.sm)) if self.sm else None,
+                    "samples": len(self.sm), "source": "nvml", "reasons": sorted(self.reasons)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -98,7 +145,25 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "source": "nvidia-smi", "reasons": sorted(reasons)}
+
+
+class _OutRing:
+    """Result-block allocator handed to the engine (FrustumEngine.out_alloc): consecutive plans get
+    consecutive slots of one buffer."""
+
+    def __init__(self, slots):
+        self.slots, self.buf, self.i = slots, None, 0
+
+    def __call__(self, n, device):
+        import torch
+        if self.buf is None:
+            self.n = n
+            self.buf = torch.empty(self.slots * n, dtype=torch.float32, device=device)
+        assert n == self.n and self.i < self.slots, "ring holds one result block per in-flight plan"
+        v = self.buf[self.i * n: (self.i + 1) * n]
+        self.i += 1
+        return v
 
 
 def host_threads():
@@ -193,6 +258,7 @@ def main():
                     help="1: TF32 tensor cores (tcgen05) — the arithmetic cuDNN uses by default; 0: fp32 FMA")
     ap.add_argument("--pool-mb", type=float, default=160.0, help="distinct input pool size (> L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-group", type=int, default=1, help="N>1: steps covered by one result all-gather")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "8")),
                     help="forwards in flight: steps are issued round-robin on this many CUDA streams")
     args = ap.parse_args()
@@ -240,10 +306,16 @@ def main():
     nstream = max(1, args.streams)
     streams = [torch.cuda.Stream(device=dev) for _ in range(nstream)]
     eng = model.engine()
+    if world > 1:
+        # N>1: the result blocks of all in-flight plans live in ONE ring, so that a group of consecutive
+        # steps is all-gathered by a single collective
+        ring = _OutRing(nstream)
+        eng.out_alloc = ring
     plans = []
     for st in streams:
         with torch.cuda.stream(st):
             plans.append(eng.plan(B, one["point_cloud"].shape[2], T))
+    eng.out_alloc = None
     plan = plans[0]
     # every pool entry is one packed block in the engine's input layout (one staging copy per step)
     host_pool, dev_pool = [], []
@@ -256,34 +328,47 @@ def main():
         dviews = {k: dflat[off: off + ref.numel()].view(ref.shape)
                   for k, off, ref in zip(keys, plan._in_offs, [plan.in_pc] + plan.in_centers + [plan.in_onehot])}
         dev_pool.append(dviews)
-    if world > 1:
-        gather_bufs = [torch.empty((world,) + tuple(pl.out_flat.shape), dtype=torch.float32, device=dev)
-                       for pl in plans]
-
-    # N>1: the per-rank result blocks are all-gathered (NCCL over NVLink) on ONE communication stream,
-    # in step order on every rank (collectives of one communicator must not race on several streams);
-    # stream k waits for "its" gather before overwriting the output block in step i + nstream.
+    # N>1: the per-rank result blocks are all-gathered (NCCL over NVLink) on ONE communication stream, in
+    # step order on every rank (collectives of one communicator must not race on several streams).  One
+    # collective covers `--gather-group` consecutive steps (default 1: measured on 2 GPUs, groups of 4 leave the
+    # HBM-resident rate unchanged within noise and cost ~10 % of the e2e rate - bigger bubbles behind the D2H
+    # copies); the streams of a group wait for "their" gather before overwriting their result blocks.
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    gather_done = [None] * nstream
+    G = max(1, min(nstream, args.gather_group))
+    ngroup = (nstream + G - 1) // G
+    gather_done = [None] * ngroup
+    if world > 1:
+        n_out = plans[0].out_flat.numel()
+        assert all(pl.out_flat.data_ptr() == ring.buf.data_ptr() + 4 * n_out * k for k, pl in enumerate(plans))
+        group_src = [ring.buf[g * G * n_out: min(nstream, (g + 1) * G) * n_out] for g in range(ngroup)]
+        gather_bufs = [torch.empty((world, src.numel()), dtype=torch.float32, device=dev) for src in group_src]
+    n_gathers = [0]
+    no_comm = os.environ.get("FCN_BENCH_NO_COMM") == "1"   # diagnostics: replicas without the result gather
 
-    def gather(k):
-        ev = torch.cuda.Event()
-        ev.record(streams[k])
-        comm_stream.wait_event(ev)
+    def gather(g):
+        for k in range(g * G, min(nstream, (g + 1) * G)):
+            comm_stream.wait_stream(streams[k])
         with torch.cuda.stream(comm_stream):
-            dist.all_gather_into_tensor(gather_bufs[k], plans[k].out_flat)
+            dist.all_gather_into_tensor(gather_bufs[g], group_src[g])
             done = torch.cuda.Event()
             done.record(comm_stream)
-        gather_done[k] = done
+        gather_done[g] = done
+        n_gathers[0] += 1
 
-    def step_resident(i, comm=True):
+    def after_step(i, last):
+        """Issue the gather of step i's group when the group is complete (or the run ends)."""
+        k = i % nstream
+        if k % G == G - 1 or k == nstream - 1 or last:
+            gather(k // G)
+
+    def step_resident(i, comm=True, last=False):
         k = i % nstream
         with torch.cuda.stream(streams[k]):
-            if world > 1 and gather_done[k] is not None:
-                streams[k].wait_event(gather_done[k])
+            if world > 1 and gather_done[k // G] is not None:
+                streams[k].wait_event(gather_done[k // G])
             out = model(dev_pool[i % npool])
-        if world > 1 and comm:
-            gather(k)
+        if world > 1 and comm and not no_comm:
+            after_step(i, last)
         return out
 
     def join_streams():
@@ -312,7 +397,7 @@ def main():
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     for i in range(args.warmup):
-        step_resident(i)
+        step_resident(i, last=(i == args.warmup - 1))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -322,7 +407,7 @@ def main():
     e0.record()
     fork_streams()
     for i in range(args.steps):
-        step_resident(args.warmup + i)
+        step_resident(args.warmup + i, last=(i == args.steps - 1))
     join_streams()
     e1.record()
     barrier()
@@ -349,24 +434,24 @@ def main():
 
     in_views = [pl.input_views() for pl in plans]
 
-    def step_e2e(i):
+    def step_e2e(i, last=False):
         k = i % nstream
         with torch.cuda.stream(streams[k]):
-            if world > 1 and gather_done[k] is not None:
-                streams[k].wait_event(gather_done[k])
+            if world > 1 and gather_done[k // G] is not None:
+                streams[k].wait_event(gather_done[k // G])
             plans[k].in_flat.copy_(host_pool[i % npool], non_blocking=True)    # H2D of this step's inputs
             model(in_views[k])                                                 # public API, zero-copy staging
             host_outs[k].copy_(plans[k].out_flat, non_blocking=True)           # D2H of the 6-tuple block
-        if world > 1:
-            gather(k)
+        if world > 1 and not no_comm:
+            after_step(i, last)
 
     for i in range(args.warmup):
-        step_e2e(i)
+        step_e2e(i, last=(i == args.warmup - 1))
     barrier()
     e0.record()
     fork_streams()
     for i in range(args.steps):
-        step_e2e(args.warmup + i)
+        step_e2e(args.warmup + i, last=(i == args.steps - 1))
     join_streams()
     e1.record()
     barrier()
@@ -413,7 +498,10 @@ def main():
             "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
             "l2": "inputs cycle through a %d-batch pool (%.0f MB > 126 MB L2); weights/workspaces stay L2-resident"
                   % (npool, npool * step_in_bytes / 1e6),
-            "cuda_graph": True, "precision": roofline["precision"], "streams_in_flight": nstream},
+            "cuda_graph": True, "precision": roofline["precision"], "streams_in_flight": nstream,
+            "collective": ("none (single GPU)" if world == 1 else
+                           "NCCL all_gather of the per-rank result blocks, one per %d steps (%d issued in this run)"
+                           % (G, n_gathers[0]))},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(plan.in_flat.numel() * 4),
                 "d2h_bytes_per_step": d2h_bytes},
         "host_issue_us_per_step": host_us,

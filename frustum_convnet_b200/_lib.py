@@ -14,7 +14,7 @@ MAX_SCALES = 8
 MAX_SEGS = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfrustum_b200.so")
+LIB_PATH = os.environ.get("FCN_LIB_PATH") or os.path.join(_HERE, "libfrustum_b200.so")   # override: kernel-variant experiments
 
 
 class GroupArgs(C.Structure):

@@ -244,6 +244,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
             }
         }
+        pdl_launch_dependents_late();   // both CTAs: every MMA of this pair is issued / relayed
     } else {
         // ================= compute / epilogue warps (both CTAs, own 128-row tile) =================
         const int q = warp & 3, h = warp >> 2;

@@ -106,6 +106,9 @@ class FrustumEngine:
         self.mean_size = torch.tensor(DATASET_INFO[dataset].MEAN_SIZE_ARRAY, dtype=torch.float32,
                                       device=self.device)
         self._plans: Dict[tuple, "_Plan"] = {}
+        # optional `f(numel, device) -> fp32 tensor` supplying the result block of new plans (lets a caller
+        # place the blocks of several in-flight plans in one buffer, e.g. for one all-gather over all of them)
+        self.out_alloc = None
         self.pack(state_dict)
 
     # ------------------------------------------------------------------ weight packing
@@ -298,7 +301,9 @@ class _Plan:
         T2 = T[1]
         # the six outputs of det_base.py:411 are views into one flat block (single all-gather / D2H)
         widths_out = (2, 3, 1, 3, eng.num_bins, eng.num_size)
-        self.out_flat = torch.empty(B * T2 * sum(widths_out), dtype=f32, device=dev)
+        n_out = B * T2 * sum(widths_out)
+        self.out_flat = (eng.out_alloc(n_out, dev) if eng.out_alloc is not None
+                         else torch.empty(n_out, dtype=f32, device=dev))
         outs, off = [], 0
         for wd in widths_out:
             n = B * T2 * wd
