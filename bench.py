@@ -181,7 +181,7 @@ def host_threads():
     return n
 
 
-def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234):
+def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234, min_seconds=0.0):
     """frustums/s of the reference algorithm on host CPUs (oracle port, all host threads)."""
     import torch
     from frustum_convnet_b200 import config, synth
@@ -208,11 +208,11 @@ def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234):
     for _ in range(warm):
         run()
     ts = []
-    for _ in range(iters):
+    while len(ts) < iters or (sum(ts) < min_seconds and len(ts) < 400):
         t0 = time.perf_counter()
         run()
         ts.append(time.perf_counter() - t0)
-    return sample_B / float(np.median(ts)), float(np.sum(ts)), n
+    return sample_B / float(np.median(ts)), float(np.sum(ts)), n, len(ts)
 
 
 def workload_name(workload, B):
@@ -228,7 +228,7 @@ def run_reference(args, rank, world):
         return
     sample_B = min(args.batch, 8)
     t0 = time.perf_counter()
-    rate, busy, n = cpu_reference_rate(args.workload, sample_B, args.steps, max(args.warmup, 1))
+    rate, busy, n, _ = cpu_reference_rate(args.workload, sample_B, args.steps, max(args.warmup, 1))
     ms = 1e3 * sample_B / rate
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
@@ -514,10 +514,10 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         sample_B = min(B, 8)
-        rate, busy, n = cpu_reference_rate(args.workload, sample_B, iters=5, warm=1)
+        rate, busy, n, nf = cpu_reference_rate(args.workload, sample_B, iters=5, warm=1, min_seconds=12.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
-                                "sample": "5 forwards of %d frustums (%.1f s of CPU work), oracle port on torch CPU fp32"
-                                          % (sample_B, busy)}
+                                "sample": "%d forwards of %d frustums (%.1f s of CPU work), oracle port on torch CPU fp32"
+                                          % (nf, sample_B, busy)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

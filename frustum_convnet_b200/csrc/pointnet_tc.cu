@@ -22,8 +22,6 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_COMPUTE_WARPS = 8;
 constexpr int TC_THREADS = (TC_COMPUTE_WARPS + 2) * 32;
 constexpr int TC_STAGE_BYTES = 16384;
-constexpr int TC_SLAB_COLS = 32;              // epilogue-3 transposition slab: 32 rows x 32 columns per warp
-constexpr int TC_SLAB_LD = TC_SLAB_COLS + 4;  // +4 floats: conflict-free float4 row writes / column reads
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -45,10 +43,9 @@ struct TcCfg {
     static constexpr bool RESIDENT = JOBS <= NSTAGE;
     // Small-channel scales are latency-bound per tile (tiny MMAs, long SIMT phases): run TWO CTAs per SM
     // so that one CTA's epilogue overlaps the other's loads/MMAs.  That needs <= 113 KB of shared memory
-    // (16-row two-pass transposition slab) and <= 256 TMEM columns (single acc3 buffer: with one
-    // 128-column chunk per tile the second buffer never overlapped anything).
+    // and <= 256 TMEM columns (single acc3 buffer: with one 128-column chunk per tile the second buffer
+    // never overlapped anything).
     static constexpr int CTAS_PER_SM = (C1 <= 64) ? 2 : 1;
-    static constexpr int SLAB_ROWS = (CTAS_PER_SM == 2) ? 16 : 32;
     static constexpr int TMEM_COLS = (CTAS_PER_SM == 2) ? 256 : 512;
     static constexpr int ACC3_COL = (CTAS_PER_SM == 2) ? 128 : 256;
     static constexpr int ACC3_BUFS = (CTAS_PER_SM == 2) ? 1 : 2;
@@ -65,8 +62,7 @@ struct TcCfg {
     static constexpr int OFF_B2 = OFF_W1 + C1 * 16;
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;                 // int sect[128]
-    static constexpr int OFF_SLAB = OFF_SECT + 2 * TC_ROWS * 4;      // per-warp [32][TC_SLAB_LD] fp32
-    static constexpr int OFF_BAR = OFF_SLAB + TC_COMPUTE_WARPS * SLAB_ROWS * TC_SLAB_LD * 4;
+    static constexpr int OFF_BAR = OFF_SECT + 2 * TC_ROWS * 4;
     static constexpr int NBAR = 2 * NSTAGE + KBMAX + 1 + 4;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
@@ -145,7 +141,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     } else if (warp == TC_COMPUTE_WARPS) {
         // ================= MMA issuer: warp-uniform control flow, elected lane issues =================
         constexpr uint32_t idesc2 = make_idesc_tf32(128, Cfg::N2);
-        constexpr uint32_t idesc3 = make_idesc_tf32(128, Cfg::N3);
+        constexpr uint32_t idesc3 = make_idesc_tf32(Cfg::N3, TC_ROWS);   // D3^T: [N3 channels] x [128 rows]
         const uint64_t adesc0 = make_desc_sw128(sA_addr), bdesc0 = make_desc_sw128(sW_addr);
         uint32_t job = 0, chunk = 0;
         bool w_ready = false;
@@ -204,8 +200,8 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         const uint64_t ad = adesc0 + (uint64_t)(kb * ((TC_ROWS * 128) >> 4));
                         const uint64_t bd = bdesc0 + (uint64_t)(Cfg::stage_off(st) >> 4);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_tf32(tmem_base + Cfg::ACC3_COL + buf * 128, ad + 2 * k, bd + 2 * k, idesc3, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k)   // transposed product: M = channels (W3 stage), N = rows (A2)
+                            mma_tf32(tmem_base + Cfg::ACC3_COL + buf * 128, bd + 2 * k, ad + 2 * k, idesc3, (kb | k) != 0);
                         if (!Cfg::RESIDENT) mma_commit(&w_empty[st]);
                     }
                     __syncwarp();
@@ -240,7 +236,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             float4 *recs = recs_all + (it & 1) * TC_ROWS;
             int *sect_s = sect_all + (it & 1) * TC_ROWS;
             float4 rec = rec_next;
-            const bool valid = row < nrows;
             if (h == 0) {
                 recs[row] = rec;
                 sect_s[row] = __float_as_int(rec.w) & 0x7fffffff;
@@ -254,13 +249,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             asm volatile("bar.sync 1, %0;\n" ::"n"(TC_COMPUTE_WARPS * 32));
             rec = recs[row];
             if (dbgc) dc[1] = clock64();
-            const int sect = __float_as_int(rec.w) & 0x7fffffff;
-            // section bookkeeping of this warp's 32 rows (rows are section-sorted): bit r of endmask
-            // is set when row r is the last valid row of its section inside this warp
-            const int nsect = __shfl_down_sync(0xffffffffu, sect, 1);
-            const bool nvalid = (row + 1) < nrows;
-            const unsigned endmask = __ballot_sync(0xffffffffu, valid && (lane == 31 || !nvalid || nsect != sect));
-
             // ---- layer 1 (fp32 FMA) -> A1, K-blocks kb = h, h+2, ...
             for (int kb = h; kb < Cfg::KB1; kb += 2) {
                 uint8_t *dst = sA + kb * (TC_ROWS * 128) + row_off;
@@ -301,58 +289,41 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[kb]);
             }
-            // ---- epilogue 3: per 128-column chunk: TMEM -> registers (thread = row), transpose 16-column
-            //      slabs through per-warp shared memory (thread = column), running max over the section's
-            //      rows, then +bias, ReLU and a coalesced integer atomicMax into the feature map
-            //      (max_r relu(x_r + b) == relu(max_r x_r + b); values >= 0 so int order == float order).
+            // ---- epilogue 3: layer 3 is computed TRANSPOSED (D3^T = W3 * A2^T), so TMEM lane = output channel
+            //      and TMEM column = tile row: after tcgen05.ld a thread holds 32 consecutive rows of ITS channel
+            //      and the max over a section's rows is a register-only running max (no shared-memory
+            //      transposition competing with the MMA's operand reads).  Section ends are warp-uniform;
+            //      +bias, ReLU, TF32 rounding commute with the max (monotone), values >= 0 so the integer
+            //      atomicMax on the float bits is exact; lanes = consecutive channels -> coalesced atomics.
             if (dbgc) dc[4] = clock64();
             int *feat = (int *)(p.out + (size_t)b * p.feat_pitch * p.ld_feat);
-            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (Cfg::SLAB_ROWS * TC_SLAB_LD);
             for (int nc = 0; nc < Cfg::NCH3; ++nc, ++chunk) {
                 const uint32_t buf = chunk % Cfg::ACC3_BUFS;
                 mbar_wait(&acc3_full[buf], (chunk / Cfg::ACC3_BUFS) & 1);
                 if (dbgc && nc < 5) dc[5 + 2 * nc] = clock64();
                 tc_fence_after();
+                const int c = nc * Cfg::N3 + q * 32 + lane;     // this thread's output channel
+                const float bias = b3s[c];
+                float run = -INFINITY;                           // carried across the warp's two row groups
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
-                    const int col0 = h * 64 + half * 32;
+                    const int g0 = (h * 2 + half) * 32;          // first tile row of this group
                     uint32_t v[32];
-                    tmem_ld32(lane_taddr + Cfg::ACC3_COL + buf * 128 + col0, v);
+                    tmem_ld32(lane_taddr + Cfg::ACC3_COL + buf * 128 + g0, v);
+                    const int rg = g0 + lane;                    // section ends inside rows [64h, 64h+64)
+                    const int sg = sect_s[rg], sn = sect_s[(rg + 1) & (TC_ROWS - 1)];
+                    const unsigned em = __ballot_sync(
+                        0xffffffffu, rg < nrows && (rg == h * 64 + 63 || rg + 1 >= nrows || sn != sg));
                     tmem_wait_ld();
-                    // lane = column; the warp walks its 32 rows section by section (bounds are warp-uniform)
-                    const int c = nc * Cfg::N3 + col0 + lane;
-                    const float bias = b3s[c];
-                    const float *col = slab + lane;
-                    constexpr int SR = Cfg::SLAB_ROWS, PASSES = 32 / SR;
-                    float run = -INFINITY;        // running max of the open section (carried across passes)
-#pragma unroll 1
-                    for (int pass = 0; pass < PASSES; ++pass) {
-                        if (PASSES == 1 || (lane / SR) == pass) {
 #pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4)
-                                *(uint4 *)(slab + (lane % SR) * TC_SLAB_LD + c4 * 4) =
-                                    make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                        }
-                        __syncwarp();
-                        unsigned em = (PASSES == 1) ? endmask : ((endmask >> (pass * SR)) & ((1u << SR) - 1u));
-                        int start = 0;
-                        while (em) {
-                            const int end = __ffs(em) - 1;
-                            em &= em - 1;
-#pragma unroll 4
-                            for (int r = start; r <= end; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
-                            const float o = to_tf32(run + bias);   // monotone: max of rounded == rounded max
+                    for (int r = 0; r < 32; ++r) {
+                        run = fmaxf(run, __uint_as_float(v[r]));
+                        if ((em >> r) & 1u) {                    // warp-uniform
+                            const float o = to_tf32(run + bias);
                             if (o > 0.f)
-                                atomicMax(feat + (size_t)sect_s[q * 32 + pass * SR + end] * p.ld_feat + c,
-                                          __float_as_int(o));
+                                atomicMax(feat + (size_t)sect_s[g0 + r] * p.ld_feat + c, __float_as_int(o));
                             run = -INFINITY;
-                            start = end + 1;
                         }
-                        if (PASSES > 1) {   // open section continues in the next pass
-#pragma unroll 4
-                            for (int r = start; r < SR; ++r) run = fmaxf(run, col[r * TC_SLAB_LD]);
-                        }
-                        __syncwarp();
                     }
                 }
                 tc_fence_before();

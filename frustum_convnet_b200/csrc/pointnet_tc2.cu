@@ -24,7 +24,6 @@ constexpr int T2_ROWS = 128;
 constexpr int T2_COMPUTE_WARPS = 8;
 constexpr int T2_THREADS = (T2_COMPUTE_WARPS + 2) * 32;
 constexpr int T2_STAGE_BYTES = 16384;          // per CTA: half of a [256 x 128 B] weight tile
-constexpr int T2_SLAB_LD = 36;
 
 template <int C1, int C2, int C3>
 struct Tc2Cfg {
@@ -41,8 +40,7 @@ struct Tc2Cfg {
     static constexpr int OFF_B2 = OFF_W1 + C1 * 16;
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;
-    static constexpr int OFF_SLAB = OFF_SECT + 2 * T2_ROWS * 4;
-    static constexpr int OFF_BAR = OFF_SLAB + T2_COMPUTE_WARPS * 32 * T2_SLAB_LD * 4;
+    static constexpr int OFF_BAR = OFF_SECT + 2 * 2 * T2_ROWS * 4;   // int sect[parity][tile of the pair][128]
     static constexpr int NBAR = 2 * NSTAGE + 2 * KBMAX + 1 + 2 + 2;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;
@@ -183,7 +181,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
         } else {
             // ================= leader: MMA issuer for both CTAs (M = 256) =================
             constexpr uint32_t idesc2 = make_idesc_tf32(256, Cfg::N2);
-            constexpr uint32_t idesc3 = make_idesc_tf32(256, Cfg::N3);
+            constexpr uint32_t idesc3 = make_idesc_tf32(Cfg::N3, 2 * T2_ROWS);   // D3^T: [256 channels] x [2 x 128 rows]
             const uint64_t adesc0 = make_desc_sw128(sA_addr), bdesc0 = make_desc_sw128(sW_addr);
             uint32_t job = 0;
             const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && lane == 0;
@@ -232,8 +230,8 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                             const uint64_t ad = adesc0 + (uint64_t)(kb * ((T2_ROWS * 128) >> 4));
                             const uint64_t bd = bdesc0 + (uint64_t)(st * (T2_STAGE_BYTES >> 4));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                mma_tf32_2cta(tmem_base + dcol, ad + 2 * k, bd + 2 * k, idesc3, (kb | k) != 0);
+                            for (int k = 0; k < 4; ++k)   // transposed: M = 256 channels (W3), N = 2 x 128 rows (A2)
+                                mma_tf32_2cta(tmem_base + dcol, bd + 2 * k, ad + 2 * k, idesc3, (kb | k) != 0);
                             mma_commit_2cta(&w_empty[st]);
                         }
                         __syncwarp();
@@ -252,41 +250,36 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const int rx = row & 7;
-        auto tile_of = [&](int it) -> int4 {
-            const int tile = 2 * (cluster_id + it * nclusters) + (int)rank;
+        auto tile_of = [&](int it, uint32_t r) -> int4 {
+            const int tile = 2 * (cluster_id + it * nclusters) + (int)r;
             return tile < ntiles ? tiles[tile] : make_int4(0, 0, 0, 0);   // odd tile count: empty partner tile
         };
-        int4 td_next = tile_of(0);
-        float4 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h == 0 && row < td_next.z)
-            rec_next = ((const float4 *)p.rows + (size_t)td_next.x * p.row_cap + td_next.y)[row];
+        // h == 0 warps stage the records of this CTA's tile (layer 1), h == 1 warps the section ids of the
+        // partner's tile (epilogue 3 drains BOTH tiles' rows for this CTA's half of the channels)
+        auto rec_of = [&](const int4 &t) -> float4 {
+            return row < t.z ? ((const float4 *)p.rows + (size_t)t.x * p.row_cap + t.y)[row]
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        int4 td_next = tile_of(0, rank), tdp_next = tile_of(0, rank ^ 1u);
+        float4 rec_next = rec_of(h == 0 ? td_next : tdp_next);
         const bool dbgc = p.dbg_clocks != nullptr && blockIdx.x == 0 && tid == 0;
         for (int it = 0; it < my_pairs; ++it) {
             const uint32_t par = it & 1;
             long long *dc = p.dbg_clocks + 4096 + 16 * it;
             if (dbgc) dc[0] = clock64();
-            const int4 td = td_next;
-            const int b = td.x, nrows = td.z;
+            const int4 td = td_next, tdp = tdp_next;
             float4 *recs = recs_all + (it & 1) * T2_ROWS;
-            int *sect_s = sect_all + (it & 1) * T2_ROWS;
+            int *sect_s = sect_all + (it & 1) * (2 * T2_ROWS);   // [tile of the pair][row]
             float4 rec = rec_next;
-            const bool valid = row < nrows;
-            if (h == 0) {
-                recs[row] = rec;
-                sect_s[row] = __float_as_int(rec.w) & 0x7fffffff;
-            }
+            if (h == 0) recs[row] = rec;
+            sect_s[((h == 0) ? rank : (rank ^ 1u)) * T2_ROWS + row] = __float_as_int(rec.w) & 0x7fffffff;
             if (it + 1 < my_pairs) {
-                td_next = tile_of(it + 1);
-                rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (h == 0 && row < td_next.z)
-                    rec_next = ((const float4 *)p.rows + (size_t)td_next.x * p.row_cap + td_next.y)[row];
+                td_next = tile_of(it + 1, rank);
+                tdp_next = tile_of(it + 1, rank ^ 1u);
+                rec_next = rec_of(h == 0 ? td_next : tdp_next);
             }
             asm volatile("bar.sync 1, %0;\n" ::"n"(T2_COMPUTE_WARPS * 32));
             rec = recs[row];
-            const int sect = __float_as_int(rec.w) & 0x7fffffff;
-            const int nsect = __shfl_down_sync(0xffffffffu, sect, 1);
-            const bool nvalid = (row + 1) < nrows;
-            const unsigned endmask = __ballot_sync(0xffffffffu, valid && (lane == 31 || !nvalid || nsect != sect));
 
             // ---- layer 1 (fp32 FMA) -> A1
             for (int kb = h; kb < Cfg::KB1; kb += 2) {
@@ -328,43 +321,45 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&a2_ready[kb], 0);
             }
-            // ---- epilogue 3: 256-column chunks; warp (q,h) drains rows 32q.. x columns 128h..
+            // ---- epilogue 3: layer 3 is computed TRANSPOSED (D3^T = W3 * A2^T): TMEM lane = output channel
+            //      (this CTA owns channels [128*rank, 128*rank+128) of the 256-wide chunk), TMEM column = row
+            //      (columns [0,128) = tile of rank 0, [128,256) = tile of rank 1).  Warp (q,h) drains channels
+            //      32q.. for the 128 rows of tile h: a thread holds 32 consecutive rows of ITS channel, the
+            //      section max is a register-only running max (carried across the four 32-row groups), the
+            //      section ends are warp-uniform, and lanes = consecutive channels -> coalesced atomics.
             if (dbgc) dc[4] = clock64();
-            int *feat = (int *)(p.out + (size_t)b * p.feat_pitch * p.ld_feat);
-            float *slab = (float *)(smem + Cfg::OFF_SLAB) + warp * (32 * T2_SLAB_LD);
+            const int4 tdt = ((uint32_t)h == rank) ? td : tdp;
+            const int nrows_t = tdt.z;
+            int *feat = (int *)(p.out + (size_t)tdt.x * p.feat_pitch * p.ld_feat);
+            const int *sect_t = sect_s + h * T2_ROWS;
             for (int nc = 0; nc < Cfg::NCH3; ++nc) {
                 const uint32_t dcol = nc == 0 ? 256u : 0u;
                 mbar_wait(&acc3_full[nc], par);
                 if (dbgc) dc[5 + 2 * nc] = clock64();
                 tc_fence_after();
+                const int c = nc * Cfg::N3 + (int)rank * T2_ROWS + q * 32 + lane;   // this thread's output channel
+                const float bias = b3s[c];
+                float run = -INFINITY;
 #pragma unroll 1
                 for (int part = 0; part < 4; ++part) {
-                    const int col0 = h * 128 + part * 32;
+                    const int g0 = part * 32;
                     uint32_t v[32];
-                    tmem_ld32(lane_taddr + dcol + col0, v);
+                    tmem_ld32(lane_taddr + dcol + h * T2_ROWS + g0, v);
+                    const int rg = g0 + lane;
+                    const int sg = sect_t[rg], sn = sect_t[(rg + 1) & (T2_ROWS - 1)];
+                    const unsigned em = __ballot_sync(
+                        0xffffffffu, rg < nrows_t && (rg == T2_ROWS - 1 || rg + 1 >= nrows_t || sn != sg));
                     tmem_wait_ld();
-                    const int c = nc * Cfg::N3 + col0 + lane;
-                    const float bias = b3s[c];
-                    const float *col = slab + lane;
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4)
-                        *(uint4 *)(slab + lane * T2_SLAB_LD + c4 * 4) =
-                            make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-                    __syncwarp();
-                    unsigned em = endmask;
-                    int start = 0;
-                    while (em) {
-                        const int end = __ffs(em) - 1;
-                        em &= em - 1;
-                        float run = col[start * T2_SLAB_LD];
-#pragma unroll 4
-                        for (int r = start + 1; r <= end; ++r) run = fmaxf(run, col[r * T2_SLAB_LD]);
-                        const float o = to_tf32(run + bias);
-                        if (o > 0.f)
-                            atomicMax(feat + (size_t)sect_s[q * 32 + end] * p.ld_feat + c, __float_as_int(o));
-                        start = end + 1;
+                    for (int r = 0; r < 32; ++r) {
+                        run = fmaxf(run, __uint_as_float(v[r]));
+                        if ((em >> r) & 1u) {                    // warp-uniform
+                            const float o = to_tf32(run + bias);
+                            if (o > 0.f)
+                                atomicMax(feat + (size_t)sect_t[g0 + r] * p.ld_feat + c, __float_as_int(o));
+                            run = -INFINITY;
+                        }
                     }
-                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();
