@@ -97,22 +97,28 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _poll(self):
+    def sample_now(self):
+        """One synchronous sample (called from the issuing thread in the middle of a timed loop, so that short
+        regions are covered even if the polling thread is starved of the GIL)."""
         nv = self.nvml
-        flags = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
-                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
-                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        if nv is None:
+            return
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                              ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                              ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
         while self.run:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for name, bit in flags:
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.002)
+            self.sample_now()
+            time.sleep(0.005)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -400,6 +406,7 @@ def main():
         step_resident(i, last=(i == args.warmup - 1))
     barrier()
     sampler = ClockSampler(local_rank)
+    sample_at = {args.steps // 4, args.steps // 2, (3 * args.steps) // 4}
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -408,11 +415,12 @@ def main():
     fork_streams()
     for i in range(args.steps):
         step_resident(args.warmup + i, last=(i == args.steps - 1))
+        if rank == 0 and i in sample_at:
+            sampler.sample_now()
     join_streams()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -452,6 +460,8 @@ def main():
     fork_streams()
     for i in range(args.steps):
         step_e2e(args.warmup + i, last=(i == args.steps - 1))
+        if rank == 0 and i in sample_at:
+            sampler.sample_now()
     join_streams()
     e1.record()
     barrier()
@@ -459,6 +469,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (float(t.item()) / args.steps * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None    # samples cover both timed regions (resident + e2e)
 
     # ---- per-kernel timing of the eager launch sequence (CUDA events on the launching stream)
     kt = plan.time_kernels(dev_pool, iters=20) if rank == 0 else None

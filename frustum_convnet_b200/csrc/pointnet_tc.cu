@@ -314,17 +314,15 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     const int sg = sect_s[rg], sn = sect_s[(rg + 1) & (TC_ROWS - 1)];
                     const unsigned em = __ballot_sync(
                         0xffffffffu, rg < nrows && (rg == h * 64 + 63 || rg + 1 >= nrows || sn != sg));
+                    if (dbgc && nc == 0) dc[9 + 3 * half] = clock64();
                     tmem_wait_ld();
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        run = fmaxf(run, __uint_as_float(v[r]));
-                        if ((em >> r) & 1u) {                    // warp-uniform
-                            const float o = to_tf32(run + bias);
-                            if (o > 0.f)
-                                atomicMax(feat + (size_t)sect_s[g0 + r] * p.ld_feat + c, __float_as_int(o));
-                            run = -INFINITY;
-                        }
-                    }
+                    if (dbgc && nc == 0) dc[10 + 3 * half] = clock64();
+                    section_max32<(C1 <= 128)>(v, em, run, [&](float m, int end) {
+                        const float o = to_tf32(m + bias);
+                        if (o > 0.f)
+                            atomicMax(feat + (size_t)sect_s[g0 + end] * p.ld_feat + c, __float_as_int(o));
+                    });
+                    if (dbgc && nc == 0) dc[11 + 3 * half] = clock64();
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -350,16 +350,11 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     const unsigned em = __ballot_sync(
                         0xffffffffu, rg < nrows_t && (rg == T2_ROWS - 1 || rg + 1 >= nrows_t || sn != sg));
                     tmem_wait_ld();
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        run = fmaxf(run, __uint_as_float(v[r]));
-                        if ((em >> r) & 1u) {                    // warp-uniform
-                            const float o = to_tf32(run + bias);
-                            if (o > 0.f)
-                                atomicMax(feat + (size_t)sect_t[g0 + r] * p.ld_feat + c, __float_as_int(o));
-                            run = -INFINITY;
-                        }
-                    }
+                    section_max32<(C1 <= 128)>(v, em, run, [&](float m, int end) {
+                        const float o = to_tf32(m + bias);
+                        if (o > 0.f)
+                            atomicMax(feat + (size_t)sect_t[g0 + end] * p.ld_feat + c, __float_as_int(o));
+                    });
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -40,4 +40,4 @@ for j, r in enumerate(jobs[:56]):
     print("%3d %8d | %6d %6d %6d" % (j, r[0] - base, r[1] - r[0], r[2] - r[1], r[3] - r[2]))
 print("compute warp 0 per tile: start recs_ready | L1_done->acc2wait acc2_ready epi2_done | chunk: acc3_ready epi3_done ...")
 for r in tiles:
-    print(" ".join("%8d" % (x - base if x > 0 else -1) for x in r[:14]))
+    print(" ".join("%8d" % (x - base if x > 0 else -1) for x in r[:16]))
