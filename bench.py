@@ -474,6 +474,25 @@ def main():
     # ---- per-kernel timing of the eager launch sequence (CUDA events on the launching stream)
     kt = plan.time_kernels(dev_pool, iters=20) if rank == 0 else None
 
+    # ---- latency of ONE forward at a time (single stream, graph replay): p10 / median / p90 over 100 calls
+    latency = None
+    if rank == 0:
+        try:
+            torch.cuda.synchronize()
+            with torch.cuda.stream(streams[0]):
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                       for _ in range(100)]
+                for j, (a, b) in enumerate(evs):
+                    a.record()
+                    model(dev_pool[j % npool])
+                    b.record()
+                    b.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in evs)
+            latency = {"p10_ms": ts[10], "median_ms": ts[50], "p90_ms": ts[90],
+                       "note": "one forward of %d frustums at a time, single stream, CUDA-graph replay" % B}
+        except Exception as e:   # informative only: never lose the bench line over it
+            latency = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -515,7 +534,7 @@ def main():
                            % (G, n_gathers[0]))},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(plan.in_flat.numel() * 4),
                 "d2h_bytes_per_step": d2h_bytes},
-        "host_issue_us_per_step": host_us,
+        "host_issue_us_per_step": host_us, "latency": latency,
         "gpu_launches": kt["launches_per_step"] * args.steps,
         "launches_per_step": kt["launches_per_step"],
         "roofline": roofline, "hbm": hbm, "clocks": clocks,
