@@ -83,6 +83,7 @@ SIGNATURES = {
     "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _I, _P, _P, _P]),
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
     "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
+    "fcn_rbbox_iou_3d_pair": (_I, [_I, _P, _P, _P, _F, _P, _P]),
 }
 
 _lib = None

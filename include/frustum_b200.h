@@ -189,6 +189,19 @@ FCN_API int fcn_btc_to_bct(int B, int C, int T, int pitch, int ld, const float *
 FCN_API int fcn_selftest_umma(int N, int K, const float *A, const void *w_img, float *D,
                               fcn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (6) Train-branch metric ("next" row 8(f)-1): pairwise rotated-box IoU on the device.  Replaces the CPU
+ *     Boost.Geometry call rbbox_iou_3d_pair (ops/pybind11/box_ops.h:173-260) and the device->host copy of
+ *     the boxes in front of it (models/det_base.py:494-495).
+ *     corners, qcorners: (M, 8, 3) fp32 box corners in the order of get_box3d_corners_helper
+ *     (models/model_util.py:48-72), 16-byte aligned;  iou: (M, 2) = [BEV IoU, 3-D IoU] per pair, zeros when
+ *     the bird's-eye-view polygons do not overlap (box_ops.h:199,226);  stats (optional, may be NULL): 3 floats
+ *     = mean BEV IoU, mean 3-D IoU, fraction of pairs with 3-D IoU >= iou_thresh (det_base.py:497-500),
+ *     reduced in a fixed order (deterministic).  M == 0 writes zeros to stats.
+ * ------------------------------------------------------------------------------------------ */
+FCN_API int fcn_rbbox_iou_3d_pair(int M, const float *corners, const float *qcorners, float *iou,
+                                  float iou_thresh, float *stats, fcn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
