@@ -39,6 +39,21 @@ def test_argument_validation_without_gpu():
     assert lib.fcn_decode_eval(1, 1, 1, 8, 12, 3, None, None, None, None, None, None, None, None, None, None) == -1
     with pytest.raises(RuntimeError):
         _lib.call("fcn_conv_gemm", None, None)
+    # rotated-box IoU entry: size / NULL / alignment checks come before the launch
+    assert lib.fcn_rbbox_iou_3d_pair(-1, None, None, None, 0.5, None, None) == -1
+    assert lib.fcn_rbbox_iou_3d_pair(4, None, None, None, 0.5, None, None) == -1
+    assert b"NULL" in lib.fcn_last_error()
+    buf = np.zeros(64, dtype=np.float32)
+    base = buf.ctypes.data + (-buf.ctypes.data) % 16          # a 16-byte aligned host address
+    assert lib.fcn_rbbox_iou_3d_pair(1, base + 4, base, base, 0.5, None, None) == -1
+    assert b"aligned" in lib.fcn_last_error()
+    assert lib.fcn_rbbox_iou_3d_pair(0, None, None, None, 0.5, None, None) == 0   # nothing to do, no stats
+
+
+def test_box_iou_wrapper_rejects_cpu_tensors_and_bad_shapes():
+    from frustum_convnet_b200.box_iou import rbbox_iou_3d_pair
+    with pytest.raises(RuntimeError):
+        rbbox_iou_3d_pair(torch.zeros(2, 8, 3), torch.zeros(2, 8, 3))
 
 
 def test_cpu_tensors_are_rejected_like_the_reference():
