@@ -33,7 +33,12 @@ struct Tc2Cfg {
     static constexpr int JOBS2 = KB1, JOBS3 = NCH3 * KB2, JOBS = JOBS2 + JOBS3;
     static constexpr int HALF2 = (N2 / 2) * 128, HALF3 = (N3 / 2) * 128;   // bytes per CTA per job
     static constexpr int A_BYTES = T2_ROWS * (C1 > C2 ? C1 : C2) * 4;
-    static constexpr int NSTAGE = (C1 >= 256) ? 3 : 6;
+    // weight-stage ring depth; the transposed epilogue freed the 36 KB transposition slab, so the 256-channel
+    // configuration now also fits 5 stages (A/B knob: scripts/build_variant.sh t2s5 -DFCN_T2_NSTAGE=5)
+#ifndef FCN_T2_NSTAGE
+#define FCN_T2_NSTAGE 3
+#endif
+    static constexpr int NSTAGE = (C1 >= 256) ? FCN_T2_NSTAGE : 6;
     static constexpr int OFF_W = A_BYTES;
     static constexpr int OFF_RECS = OFF_W + NSTAGE * T2_STAGE_BYTES;
     static constexpr int OFF_W1 = OFF_RECS + 2 * T2_ROWS * 16;
