@@ -10,6 +10,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// A/B knob (scripts/next_round_ab.sh): hand-pipelined shared-memory loads in the SIMT phases of the PointNet
+// kernels (layer 1 weights, epilogue-2 biases).  Same arithmetic, different instruction order.
+#ifndef FCN_SIMT_PREFETCH
+#define FCN_SIMT_PREFETCH 0
+#endif
+
 namespace fcn {
 namespace umma {
 
