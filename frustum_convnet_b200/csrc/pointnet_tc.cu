@@ -97,8 +97,12 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
     pdl_wait();                 // tile table / rows / feature map come from the grouping kernels
     pdl_launch_dependents();
     const int ntiles = min(*p.ntiles, p.max_tiles);
-    if ((int)blockIdx.x >= ntiles) return;  // whole CTA exits together: nothing was started
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tile stride of the persistent loop: the grid, or (FCN_BALANCE_ROUNDS) only as many CTAs as the round
+    // count needs - e.g. 2.4 rounds become 3 rounds on 80 % of the CTAs, the rest exit at once and leave
+    // their SMs to the kernels of the other in-flight forwards
+    const int tstride = balanced_stride(ntiles, (int)gridDim.x);
+    if ((int)blockIdx.x >= ntiles || (int)blockIdx.x >= tstride) return;  // whole CTA exits: nothing was started
+    const int my_tiles = (ntiles - (int)blockIdx.x + tstride - 1) / tstride;
 
     // ---- one-time setup
     for (int i = tid; i < C1; i += TC_THREADS)
@@ -241,7 +245,7 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 sect_s[row] = __float_as_int(rec.w) & 0x7fffffff;
             }
             if (it + 1 < my_tiles) {
-                td_next = tiles[blockIdx.x + (it + 1) * gridDim.x];
+                td_next = tiles[blockIdx.x + (it + 1) * tstride];
                 rec_next = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (h == 0 && row < td_next.z)
                     rec_next = ((const float4 *)p.rows + (size_t)td_next.x * p.row_cap + td_next.y)[row];

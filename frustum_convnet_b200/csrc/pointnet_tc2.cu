@@ -116,12 +116,13 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x >> 1;
     pdl_wait();
     pdl_launch_dependents();
     const int ntiles = min(*p.ntiles, p.max_tiles);
     const int npairs = (ntiles + 1) >> 1;
-    if (cluster_id >= npairs) return;                      // both CTAs of the pair agree
+    const int nclusters = balanced_stride(npairs, (int)(gridDim.x >> 1));   // pair stride (see umma.cuh)
+    if (cluster_id >= npairs || cluster_id >= nclusters) return;            // both CTAs of the pair agree
     const int my_pairs = (npairs - cluster_id + nclusters - 1) / nclusters;
 
     for (int i = tid; i < C1; i += T2_THREADS)

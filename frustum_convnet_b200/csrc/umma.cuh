@@ -15,6 +15,10 @@
 #ifndef FCN_SIMT_PREFETCH
 #define FCN_SIMT_PREFETCH 0
 #endif
+// A/B knob: persistent PointNet kernels use only as many CTAs (clusters) as their number of rounds needs.
+#ifndef FCN_BALANCE_ROUNDS
+#define FCN_BALANCE_ROUNDS 0
+#endif
 
 namespace fcn {
 namespace umma {
@@ -218,6 +222,14 @@ __device__ __forceinline__ void section_max32(const uint32_t (&v)[32], unsigned 
         for (int r = 0; r < 32; ++r)
             if ((mask >> r) & 1u) run = fmaxf(run, __uint_as_float(v[r]));
     }
+}
+
+// Work units `n` over at most `slots` persistent CTAs (clusters): rounds = ceil(n / slots) is fixed by the
+// grid; ceil(n / rounds) slots are enough to finish in that many rounds.  Returns the unit stride to use.
+__host__ __device__ inline int balanced_stride(int n, int slots) {
+    if (!FCN_BALANCE_ROUNDS || n <= 0 || slots <= 0) return slots;
+    const int rounds = (n + slots - 1) / slots;
+    return (n + rounds - 1) / rounds;
 }
 
 }  // namespace fcn
