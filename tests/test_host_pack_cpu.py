@@ -159,3 +159,25 @@ def test_packed_pointnet_weights_reproduce_reference_features(golden_loader, nam
         assert float((feat - ref[:, :, :C3]).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
         one_hot = torch.from_numpy(data["one_hot"]).double()
         assert torch.equal(ref[:, :, C3:], one_hot[:, None, :].expand(-1, T, -1))
+
+
+@pytest.mark.parametrize("wl", ["car", "people", "sunrgbd"])
+def test_roofline_denominators_follow_from_the_architecture(wl):
+    """bench.ALGO (algorithmic bytes and nominal FLOPs per frustum) recomputed from the layer
+    widths, section counts and sample counts - the numbers `roofline.achieved` / `hbm.achieved` are built on."""
+    import bench
+    from frustum_convnet_b200 import synth
+    cfg, w = config.load_workload(wl)
+    arch, V = w["arch"], w["num_vec"]
+    T, K, N = list(synth.section_counts(wl)), arch.nsample, synth._PRESETS[wl]["N"]
+    mac = sum(t * k * (3 * c1 + c1 * c2 + c2 * c3) for (c1, c2, c3), t, k in zip(arch.mlps, T, K))
+    for name, kind, ci, co, k, s in synth.fcn_layer_table(arch, V):
+        i = 1 if name == "block1_conv1" else int(name[5])
+        mac += T[i - 1] * ci * co * k          # conv: per output position; transposed conv: per input position
+    n_reg = 39 if arch.num_scales == 4 else 67   # det_base.py:248 / det_base_sunrgbd.py
+    mac += T[1] * arch.reg_in * (2 + n_reg)
+    n_size = 3 if arch.num_scales == 4 else 10
+    out_bytes = T[1] * (2 + 3 + 1 + 3 + 12 + n_size) * 4
+    in_bytes = (3 * N + 3 * sum(T) + V) * 4
+    assert bench.ALGO[wl]["gflop"] == pytest.approx(2 * mac / 1e9, rel=2e-4)
+    assert bench.ALGO[wl]["bytes"] == pytest.approx(in_bytes + out_bytes, rel=3e-3)
