@@ -63,21 +63,46 @@ __device__ __forceinline__ void pdl_launch_dependents_late() {
     if (FCN_PDL_MODE == 1) pdl_trigger();
 }
 
+// A/B knob: launch priority of a kernel class (kept by the graph node when captured).  `FCN_PRIO_PN` /
+// `FCN_PRIO_CONV` = integer in the device's stream-priority range (lower = scheduled first); unset = no attribute.
+// With several forwards in flight the block scheduler then places e.g. the persistent PointNet CTAs before the
+// conv CTAs of the other forwards instead of in arrival order.
+constexpr int FCN_NO_PRIORITY = -1000000;
+inline int env_priority(const char *name) {
+    const char *v = getenv(name);
+    return (v != nullptr && *v != 0) ? atoi(v) : FCN_NO_PRIORITY;
+}
+
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, Args &&...args) {
+inline cudaError_t launch_pdl_prio(int priority, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                   cudaStream_t stream, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
     static const bool no_pdl = getenv("FCN_NO_PDL") != nullptr;   // diagnostics
+    unsigned n = 0;
+    if (!no_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (priority != FCN_NO_PRIORITY) {
+        attr[n].id = cudaLaunchAttributePriority;
+        attr[n].val.priority = priority;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args &&...args) {
+    return launch_pdl_prio(FCN_NO_PRIORITY, kern, grid, block, smem, stream, std::forward<Args>(args)...);
 }
 
 }  // namespace fcn

@@ -211,7 +211,8 @@ static int launch_gm(const ConvTmaParams &P, cudaStream_t stream) {
     FCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::BYTES));
     const fcn_conv_args &a = P.a;
     dim3 grid(ceil_div(a.B * a.P_m, GM_ROWS), a.n_cols / NT);
-    FCN_CUDA(launch_pdl(kern, grid, dim3(GM_THREADS), (size_t)Cfg::BYTES, stream, P));
+    static const int prio = env_priority("FCN_PRIO_CONV");
+    FCN_CUDA(launch_pdl_prio(prio, kern, grid, dim3(GM_THREADS), (size_t)Cfg::BYTES, stream, P));
     return FCN_OK;
 }
 

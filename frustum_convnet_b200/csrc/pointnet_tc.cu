@@ -390,7 +390,8 @@ static int launch_tc(const fcn_pointnet_args &a, cudaStream_t stream) {
     int grid = sm_count() * Cfg::CTAS_PER_SM;
     if (grid > a.max_tiles) grid = a.max_tiles;
     if (grid < 1) return FCN_OK;
-    FCN_CUDA(launch_pdl(kern, dim3(grid), dim3(TC_THREADS), (size_t)Cfg::BYTES, stream, a));
+    static const int prio = env_priority("FCN_PRIO_PN");
+    FCN_CUDA(launch_pdl_prio(prio, kern, dim3(grid), dim3(TC_THREADS), (size_t)Cfg::BYTES, stream, a));
     return FCN_OK;
 }
 

@@ -427,7 +427,8 @@ static int launch_tc2(const fcn_pointnet_args &a, cudaStream_t stream) {
     const int max_pairs2 = 2 * ((a.max_tiles + 1) / 2);
     if (grid > max_pairs2) grid = max_pairs2;
     if (grid < 2) return FCN_OK;
-    FCN_CUDA(launch_pdl(kern, dim3(grid), dim3(T2_THREADS), (size_t)Cfg::BYTES, stream, a));
+    static const int prio = env_priority("FCN_PRIO_PN");
+    FCN_CUDA(launch_pdl_prio(prio, kern, dim3(grid), dim3(T2_THREADS), (size_t)Cfg::BYTES, stream, a));
     return FCN_OK;
 }
 

@@ -23,6 +23,10 @@ case "$1" in
       FCN_LIB_PATH=$PWD/frustum_convnet_b200/variants/libfrustum_b200_$n.so \
         timeout 300 python -m pytest tests/test_gpu_tc.py -x -q -m gpu 2>&1 | tail -1
     done
-    bash scripts/gpu_ab.sh -- pdl1 t2s5 spf bal gm2 both ;;
+    bash scripts/gpu_ab.sh -- pdl1 t2s5 spf bal gm2 both
+    # runtime knobs (default library): launch priority of the PointNet / conv kernels
+    for e in "FCN_PRIO_PN=-1" "FCN_PRIO_CONV=-1" "FCN_PRIO_PN=-2 FCN_PRIO_CONV=-1"; do
+      echo "== $e"; env $e bash scripts/gpu_ab.sh -- | head -1
+    done ;;
   *) echo "usage: $0 build|run"; exit 1 ;;
 esac
