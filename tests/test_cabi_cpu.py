@@ -93,3 +93,14 @@ def test_engine_weight_pack_is_a_pure_function_of_the_state_dict(golden_loader):
         tsd[p + ".1.weight"], tsd[p + ".1.bias"], False, 0.1, 1e-5)
     mine = x @ (wq * s[:, None]).t() + sh
     assert torch.allclose(ref.double(), mine, atol=1e-5)
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/frustum_b200.h is the drop-in boundary: it must compile as C99 with nothing but libc headers."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "frustum_b200.h"\nint main(void) { (void)fcn_version; return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only",
+                           "-I", os.path.join(ROOT, "include"), str(src)])
+    txt = open(os.path.join(ROOT, "include", "frustum_b200.h")).read()
+    assert "torch" not in txt.lower().replace("pytorch", "") and "at::" not in txt
