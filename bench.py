@@ -187,7 +187,7 @@ def host_threads():
     return n
 
 
-def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234, min_seconds=0.0):
+def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234, min_seconds=0.0, budget_s=None):
     """frustums/s of the reference algorithm on host CPUs (oracle port, all host threads)."""
     import torch
     from frustum_convnet_b200 import config, synth
@@ -211,6 +211,10 @@ def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234, min_seconds=0
             best = (dt, cand)
     n = best[1]
     torch.set_num_threads(n)
+    if budget_s is not None and (iters + warm) * best[0] > budget_s and sample_B > 1:
+        # keep the whole `--steps K --warmup W` run bounded: fewer frustums per step (never below one)
+        sample_B = max(1, min(sample_B, int(sample_B * budget_s / ((iters + warm) * best[0]))))
+        data = synth.make_frustums(workload, sample_B, seed=seed)
     for _ in range(warm):
         run()
     ts = []
@@ -218,7 +222,7 @@ def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234, min_seconds=0
         t0 = time.perf_counter()
         run()
         ts.append(time.perf_counter() - t0)
-    return sample_B / float(np.median(ts)), float(np.sum(ts)), n, len(ts)
+    return sample_B / float(np.median(ts)), float(np.sum(ts)), n, len(ts), sample_B
 
 
 def workload_name(workload, B):
@@ -234,7 +238,8 @@ def run_reference(args, rank, world):
         return
     sample_B = min(args.batch, 8)
     t0 = time.perf_counter()
-    rate, busy, n, _ = cpu_reference_rate(args.workload, sample_B, args.steps, max(args.warmup, 1))
+    rate, busy, n, _, sample_B = cpu_reference_rate(args.workload, sample_B, args.steps, max(args.warmup, 1),
+                                                    budget_s=150.0)
     ms = 1e3 * sample_B / rate
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
@@ -544,7 +549,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         sample_B = min(B, 8)
-        rate, busy, n, nf = cpu_reference_rate(args.workload, sample_B, iters=5, warm=1, min_seconds=12.0)
+        rate, busy, n, nf, sample_B = cpu_reference_rate(args.workload, sample_B, iters=5, warm=1, min_seconds=12.0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
                                 "sample": "%d forwards of %d frustums (%.1f s of CPU work), oracle port on torch CPU fp32"
                                           % (nf, sample_B, busy)}
