@@ -548,11 +548,15 @@ def main():
         "unique_row_fraction": kt["unique_row_fraction"],
     }
     if world == 1 and not args.no_cpu_baseline:
-        sample_B = min(B, 8)
-        rate, busy, n, nf, sample_B = cpu_reference_rate(args.workload, sample_B, iters=5, warm=1, min_seconds=12.0)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
-                                "sample": "%d forwards of %d frustums (%.1f s of CPU work), oracle port on torch CPU fp32"
-                                          % (nf, sample_B, busy)}
+        try:
+            sample_B = min(B, 8)
+            rate, busy, n, nf, sample_B = cpu_reference_rate(args.workload, sample_B, iters=5, warm=1,
+                                                             min_seconds=12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
+                                    "sample": "%d forwards of %d frustums (%.1f s of CPU work), oracle port on "
+                                              "torch CPU fp32" % (nf, sample_B, busy)}
+        except Exception as e:   # the GPU measurement above must not be lost over the CPU leg
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
