@@ -225,10 +225,10 @@ def cpu_reference_rate(workload, sample_B, iters, warm, seed=1234, min_seconds=0
     return sample_B / float(np.median(ts)), float(np.sum(ts)), n, len(ts), sample_B
 
 
-def workload_name(workload, B):
+def workload_name(workload, B, points=None):
     from frustum_convnet_b200 import config, synth
     w = config.WORKLOADS[workload]
-    N = synth._PRESETS[workload]["N"]
+    N = points or synth._PRESETS[workload]["N"]
     return "%s cfgs/%s B=%d frustums/GPU x %d pts, T=%s, forward (eval)" % (
         workload, w["yaml"], B, N, list(synth.section_counts(workload)))
 
@@ -268,6 +268,8 @@ def main():
     ap.add_argument("--precision", type=int, default=int(os.environ.get("FCN_PRECISION", "1")),
                     help="1: TF32 tensor cores (tcgen05) — the arithmetic cuDNN uses by default; 0: fp32 FMA")
     ap.add_argument("--pool-mb", type=float, default=160.0, help="distinct input pool size (> L2)")
+    ap.add_argument("--points", type=int, default=None,
+                    help="points per frustum (default: the workload's yaml value; e.g. people at 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-group", type=int, default=1, help="N>1: steps covered by one result all-gather")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "8")),
@@ -304,12 +306,12 @@ def main():
     B, S = args.batch, w["arch"].num_scales
 
     # ---- input pool larger than L2 (126 MB): distinct batches cycled through the timed loop
-    one = synth.make_frustums(args.workload, B, seed=1234 + rank)
+    one = synth.make_frustums(args.workload, B, seed=1234 + rank, N=args.points)
     keys = ["point_cloud"] + ["center_ref%d" % (i + 1) for i in range(S)] + ["one_hot"]
     step_in_bytes = int(sum(one[k].nbytes for k in keys))
     npool = max(2, int(np.ceil(args.pool_mb * 1e6 / step_in_bytes)))
     ngen = min(npool, 8)   # 8 seeded batches, the rest are per-frustum rotations of them
-    base = [synth.make_frustums(args.workload, B, seed=1234 + rank + 1000 * i) for i in range(ngen)]
+    base = [synth.make_frustums(args.workload, B, seed=1234 + rank + 1000 * i, N=args.points) for i in range(ngen)]
     T = [one["center_ref%d" % (i + 1)].shape[2] for i in range(S)]
 
     # `--streams` forwards in flight: step i runs on stream i % S with its own workspace + CUDA graph
@@ -504,7 +506,9 @@ def main():
         return
 
     peaks = load_peaks()
-    algo = ALGO[args.workload]
+    algo = dict(ALGO[args.workload])
+    if args.points:   # non-default point count: 12 B per point more/less input per frustum (FLOPs are T x K bound)
+        algo["bytes"] += 12.0 * (args.points - synth._PRESETS[args.workload]["N"])
     dom = max(kt["kernels"], key=lambda k: k["ms"])
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
@@ -529,7 +533,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32" if args.precision == 1 else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, B),
+        "config": {"workload": workload_name(args.workload, B, args.points),
             "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
             "l2": "inputs cycle through a %d-batch pool (%.0f MB > 126 MB L2); weights/workspaces stay L2-resident"
                   % (npool, npool * step_in_bytes / 1e6),
