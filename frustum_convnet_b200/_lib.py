@@ -32,6 +32,7 @@ class GroupArgs(C.Structure):
         ("idx_scratch", C.c_void_p * MAX_SCALES),
         ("feat_pitch", C.c_int * MAX_SCALES),
         ("ntiles", C.c_void_p),
+        ("force_scan", C.c_int),
     ]
 
 

@@ -77,12 +77,20 @@ FCN_HD void rbbox_iou_pair(const float *c, const float *q, float *iou) {
     }
     iou[0] = 0.f;
     iou[1] = 0.f;
+    // Degenerate boxes.  The reference hands Boost un-`correct`ed rings (box_ops.h:206-224); a ring whose signed
+    // area is not positive in Boost's clockwise convention (a decoded box with exactly one negative footprint
+    // size, e.g. from untrained weights) violates the polygon concept and bg::intersection / bg::union_ are
+    // unspecified on it.  Decision (pinned in oracle/box_iou.py and tests/test_box_iou_cpu.py): such a pair
+    // scores (0, 0) - an invalid box gets no overlap credit - which keeps 0 <= IoU_3D <= IoU_2D <= 1.  Negative
+    // HEIGHTS need no special case: `vol = max(0, area*h)` and `max(0, ymax-ymin)` (box_ops.h:242-245) already
+    // yield a zero 3-D IoU, exactly as the reference arithmetic does.
+    const float area = -shoelace_ccw(P, 4), qarea = -shoelace_ccw(Q, 4);   // clockwise positive (Boost default)
+    if (!(area > 0.f) || !(qarea > 0.f)) return;
     const int n = clip_quads(P, Q, I);
     if (n < 3) return;
     float inter = shoelace_ccw(I, n);
     inter = inter < 0.f ? -inter : inter;
     if (!(inter > 0.f)) return;
-    const float area = -shoelace_ccw(P, 4), qarea = -shoelace_ccw(Q, 4);   // clockwise positive (Boost default)
     const float uni = area + qarea - inter;
     const float ymax = c[1] < q[1] ? c[1] : q[1];                          // min of the corner-0 heights
     const float ymin = c[13] > q[13] ? c[13] : q[13];                      // max of the corner-4 heights

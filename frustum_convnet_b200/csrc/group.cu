@@ -15,13 +15,16 @@ namespace fcn {
 
 thread_local char g_err[512] = "";
 
-int sm_count() {
-    static int n = 0;
+int sm_count() {   // per device: a process may drive several GPUs
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev];
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev] = n;
     }
     return n;
 }
@@ -498,7 +501,7 @@ extern "C" int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream) {
                                                 (size_t)a.T[s] * a.K[s]);
         smem_b = need > smem_b ? need : smem_b;
     }
-    const bool force_scan = getenv("FCN_GROUP_SCAN") != nullptr;   // A-B testing of the two grouping paths
+    const bool force_scan = a.force_scan != 0;   // A-B testing of the two grouping paths (host decides)
     FCN_REQUIRE(a.B <= 65535 && a.num_scales <= 65535, "grid too large");
     if (smem_b <= 200 * 1024 && !force_scan) {
         if (smem_b > 48 * 1024)

@@ -20,13 +20,23 @@ DESIGN.md.
 """
 from __future__ import annotations
 
+import os
+import sys
+
 import numpy as np
 import torch
 import torch.nn as nn
 
-from .config import ARCH_KITTI, DATASET_INFO, ArchSpec, get_cfg
-from .engine import FrustumEngine
-from .query_depth_point import QueryDepthPoint
+# The reference selects the model file with ``cfg.MODEL.FILE`` and loads it as a TOP-LEVEL module
+# (utils/utils.py:12-25: ``sys.path.append(folder); importlib.import_module(file[:-3])``), so this file
+# must import without a parent package: absolute imports + a bootstrap that makes the package reachable.
+_PKG_PARENT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG_PARENT not in sys.path:
+    sys.path.insert(0, _PKG_PARENT)
+
+from frustum_convnet_b200.config import ARCH_KITTI, DATASET_INFO, ArchSpec, get_cfg  # noqa: E402
+from frustum_convnet_b200.engine import FrustumEngine  # noqa: E402
+from frustum_convnet_b200.query_depth_point import QueryDepthPoint  # noqa: E402
 
 __all__ = ["QueryDepthPoint", "PointNetModule", "PointNetFeat", "ConvFeatNet", "PointNetDet"]
 
@@ -54,58 +64,98 @@ def _init_kaiming(module):
             m.bias.data.zero_()
 
 
+def default_precision() -> int:
+    """Eval arithmetic of a drop-in module whose ``precision`` attribute was not set: ``FCN_PRECISION``
+    (1 = TF32 tcgen05 tensor cores — the benchmarked configuration and what cuDNN itself computes for these
+    convolutions by default; 0 = fp32 FMA everywhere)."""
+    return int(os.environ.get("FCN_PRECISION", "1"))
+
+
+def default_cuda_graph() -> bool:
+    """``FCN_CUDA_GRAPH`` (default 1): replay one CUDA graph per input shape in PointNetDet.forward."""
+    return os.environ.get("FCN_CUDA_GRAPH", "1") != "0"
+
+
 class _EngineOwner(nn.Module):
-    """Mixin: lazily (re)builds the kernel-ready weight pack when weights/device/mode change."""
+    """Mixin: lazily (re)builds the kernel-ready weight pack when weights/device/mode change.
+
+    Staleness rules: mode switches, device moves and every ``load_state_dict`` — also one issued
+    on a parent/wrapper module, which reaches this module only through ``_load_from_state_dict`` — mark the
+    pack dirty; in-place updates that go through autograd-visible tensors (optimizer steps, ``p.copy_()``)
+    bump ``Tensor._version`` and are caught by a version scan on EVERY call (a cached tensor list makes
+    the scan ~10 us).  Edits through ``.data`` (``p.data.copy_()``) bypass the version counter by
+    construction: call ``refresh()`` after them."""
 
     _engine = None
     _engine_key = None
     _engine_dirty = True
-    _engine_calls = 0
-    precision = 0  # 0: fp32 CUDA cores, 1: TF32 tensor cores for the dense layers
+    _tensor_cache = None
+    precision = None  # None: default_precision(); 0: fp32 CUDA cores, 1: TF32 tensor cores for the dense layers
+
+    def __init__(self):
+        super().__init__()
+        self.register_load_state_dict_post_hook(_mark_dirty_hook)
 
     def _engine_spec(self):  # -> (arch, num_vec, dataset, dists, num_bins, prefix)
         raise NotImplementedError
 
-    def _param_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
-            tuple((b.data_ptr(), b._version) for b in self.buffers())
+    def _tensors(self):
+        if self._tensor_cache is None:
+            self._tensor_cache = list(self.parameters()) + list(self.buffers())
+        return self._tensor_cache
 
-    # weight-pack invalidation: mode switches, device moves and load_state_dict mark the pack dirty;
-    # in-place edits of individual parameters are caught by a full version scan every 64th call
-    # (a scan per call costs ~100 us of host time, more than the whole GPU forward).
+    def _param_version(self):
+        return tuple([t._version for t in self._tensors()])
+
     def train(self, mode=True):
         self._engine_dirty = True
         return super().train(mode)
 
     def _apply(self, fn, *args, **kwargs):
         self._engine_dirty = True
+        self._tensor_cache = None
         return super()._apply(fn, *args, **kwargs)
 
-    def load_state_dict(self, *args, **kwargs):
+    def _load_from_state_dict(self, *args, **kwargs):
         self._engine_dirty = True
-        return super().load_state_dict(*args, **kwargs)
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def refresh(self):
         """Force a rebuild of the kernel-ready weight pack at the next eval forward."""
         self._engine_dirty = True
+        self._tensor_cache = None
+
+    def resolved_precision(self) -> int:
+        return default_precision() if self.precision is None else int(self.precision)
 
     def engine(self) -> FrustumEngine:
-        self._engine_calls += 1
-        if self._engine is not None and not self._engine_dirty and (self._engine_calls & 63) and \
-                self._engine.precision == self.precision:
-            return self._engine
+        prec = self.resolved_precision()
+        if self._engine is not None and not self._engine_dirty:
+            ver = self._param_version()
+            if self._engine_key[1] == prec and self._engine_key[2] == ver:
+                return self._engine
+        if getattr(self, "_is_replica", False) or next(self.parameters(), None) is None:
+            # nn.DataParallel replicas carry no parameters and share the source module's attributes
+            # (test_net_det.py:404, train_net_det.py:308): the hot path is one process per GPU instead
+            raise RuntimeError("frustum_convnet_b200 modules cannot run as nn.DataParallel replicas; launch one "
+                               "process per GPU (torchrun) — see INTEGRATION.md, multi-GPU")
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("the frustum hot path runs on CUDA only (no CPU fallback); "
                                "move the module to a B200 with .cuda()")
-        key = (dev, self.precision, self._param_version())
-        if self._engine is None or self._engine_key != key:
+        self._tensor_cache = None
+        key = (dev, prec, self._param_version())
+        if self._engine is None or self._engine_key != key or self._engine_dirty:
             arch, num_vec, dataset, dists, num_bins, prefix = self._engine_spec()
             sd = {prefix + k: v for k, v in self.state_dict().items()}
-            self._engine = FrustumEngine(arch, num_vec, dataset, dists, num_bins, sd, dev, self.precision)
+            self._engine = FrustumEngine(arch, num_vec, dataset, dists, num_bins, sd, dev, prec)
             self._engine_key = key
         self._engine_dirty = False
         return self._engine
+
+
+def _mark_dirty_hook(module, incompatible_keys):
+    module._engine_dirty = True
 
 
 class PointNetModule(_EngineOwner):
@@ -129,7 +179,7 @@ class PointNetModule(_EngineOwner):
 
     def forward(self, pc, feat, new_pc=None):
         if self.training or self.use_feature or not self.use_xyz:
-            from .train_path import pointnet_module_torch
+            from frustum_convnet_b200.train_path import pointnet_module_torch
             return pointnet_module_torch(self, pc, feat, new_pc)
         return self.engine().pointnet_module(0, pc.contiguous(), new_pc.contiguous())
 
@@ -154,7 +204,7 @@ class PointNetFeat(_EngineOwner):
 
     def forward(self, point_cloud, sample_pc, feat=None, one_hot_vec=None):
         if self.training or feat is not None or (one_hot_vec is None) != (self.num_vec == 0):
-            from .train_path import pointnet_feat_torch
+            from frustum_convnet_b200.train_path import pointnet_feat_torch
             return pointnet_feat_torch(self, point_cloud, sample_pc, feat, one_hot_vec)
         if one_hot_vec is not None:
             assert self.num_vec == one_hot_vec.shape[1]
@@ -188,7 +238,7 @@ class ConvFeatNet(_EngineOwner):
 
     def forward(self, *xs):
         if self.training:
-            from .train_path import conv_feat_net_torch
+            from frustum_convnet_b200.train_path import conv_feat_net_torch
             return conv_feat_net_torch(self, xs)
         return self.engine().conv_feat_net([x.contiguous() for x in xs])
 
@@ -220,7 +270,7 @@ class PointNetDet(_EngineOwner):
         nn.init.kaiming_uniform_(self.reg_out.weight, mode="fan_in")
         self.cls_out.bias.data.zero_()
         self.reg_out.bias.data.zero_()
-        self.use_cuda_graph = False   # replay one CUDA graph per input shape
+        self.use_cuda_graph = default_cuda_graph()   # replay one CUDA graph per input shape (FCN_CUDA_GRAPH)
         self.copy_outputs = True      # False: return views of the engine's output block (zero-copy)
 
     def _engine_spec(self):
@@ -234,7 +284,7 @@ class PointNetDet(_EngineOwner):
         has_labels = data_dicts.get("box3d_center") is not None
         if has_labels or self.training or point_cloud.shape[1] > 3:
             assert has_labels or not self.training, "Please provide labels for training."
-            from .train_path import pointnet_det_torch
+            from frustum_convnet_b200.train_path import pointnet_det_torch
             return pointnet_det_torch(self, data_dicts)
         xyz = point_cloud[:, :3, :].contiguous()
         out = self.engine().forward(xyz, [c.contiguous() for c in centers],

@@ -6,9 +6,17 @@ heads on 1024 channels.  Everything else is shared with ``det_base``.
 """
 from __future__ import annotations
 
-from . import det_base as _kitti
-from .config import ARCH_SUNRGBD
-from .det_base import PointNetModule, QueryDepthPoint, _block1d, _init_kaiming, _upblock1d
+import os
+import sys
+
+# loadable as a top-level module through the reference's import_from_file (utils/utils.py:12-25)
+_PKG_PARENT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG_PARENT not in sys.path:
+    sys.path.insert(0, _PKG_PARENT)
+
+from frustum_convnet_b200 import det_base as _kitti  # noqa: E402
+from frustum_convnet_b200.config import ARCH_SUNRGBD  # noqa: E402
+from frustum_convnet_b200.det_base import PointNetModule, QueryDepthPoint, _block1d, _init_kaiming, _upblock1d  # noqa: E402
 
 __all__ = ["QueryDepthPoint", "PointNetModule", "PointNetFeat", "ConvFeatNet", "PointNetDet"]
 

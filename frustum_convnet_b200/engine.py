@@ -64,21 +64,26 @@ def _fold_bn(sd, prefix) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 class _ConvLayer:
-    """One fcn_conv_gemm call: packed weights + symbolic segment/output description."""
+    """One fcn_conv_gemm call: packed weights + symbolic segment/output description.
+    `wt` / `bias` arrive as HOST tensors (BN folded in float64 on the CPU: one upload per operand instead of
+    ~900 tiny device launches per pack); the device copies are made here."""
 
-    def __init__(self, name, segs, K_pad, n_cols, Cout, up, relu, wt, bias, out, c_off):
+    def __init__(self, name, segs, K_pad, n_cols, Cout, up, relu, wt, bias, out, c_off, device):
         self.name, self.segs, self.K_pad, self.n_cols = name, segs, K_pad, n_cols
-        self.Cout, self.up, self.relu, self.wt, self.bias = Cout, up, relu, wt, bias
-        self.out, self.c_off = out, c_off
+        self.Cout, self.up, self.relu = Cout, up, relu
+        self.out, self.c_off, self.device = out, c_off, device
         if K_pad % 64:   # tensor-core stages are 64 K elements wide: one extra all-zero K block
-            self.wt = torch.cat([wt, torch.zeros(32, wt.shape[1], dtype=wt.dtype, device=wt.device)], 0).contiguous()
+            wt = torch.cat([wt, torch.zeros(32, wt.shape[1], dtype=wt.dtype)], 0).contiguous()
             self.K_pad = K_pad + 32
+        self._wt_host = wt
+        self.wt = wt.to(device)
+        self.bias = bias.to(device)
         self._tc = {}
 
     def tc_image(self, n_tile: int) -> torch.Tensor:
         """Pre-swizzled tensor-core stage images [n_tile][kb][n_tile rows x 128 B] (lazy, cached)."""
         if n_tile not in self._tc:
-            self._tc[n_tile] = pack_sw128(self.wt.t().contiguous(), n_tile)
+            self._tc[n_tile] = pack_sw128(self._wt_host.t().contiguous(), n_tile).to(self.device)
         return self._tc[n_tile]
 
 
@@ -98,6 +103,7 @@ class FrustumEngine:
         # 2-CTA (cta_group::2) PointNet kernel for the 256-channel scale(s): measured 57.5 -> 44.6 us on
         # pointnet_s4; no gain at 128 channels (26.2 vs 27.0 us), so those stay on the 1-CTA kernel
         self.pn_cluster = os.environ.get("FCN_PN_CLUSTER", "1") == "1"
+        self.group_scan = os.environ.get("FCN_GROUP_SCAN") is not None   # A/B: section-scan grouping kernels
         self.tile_rows = 64 if self.precision == 0 else 128
         self.out_size = reg_out_size(dataset, self.num_bins)
         self.ld_logit = _round_up(2 + self.out_size, 64)
@@ -106,6 +112,7 @@ class FrustumEngine:
         self.mean_size = torch.tensor(DATASET_INFO[dataset].MEAN_SIZE_ARRAY, dtype=torch.float32,
                                       device=self.device)
         self._plans: Dict[tuple, "_Plan"] = {}
+        self.max_plans = int(os.environ.get("FCN_MAX_PLANS", "64"))   # (shape, stream) workspaces kept alive
         # optional `f(numel, device) -> fp32 tensor` supplying the result block of new plans (lets a caller
         # place the blocks of several in-flight plans in one buffer, e.g. for one all-gather over all of them)
         self.out_alloc = None
@@ -113,8 +120,11 @@ class FrustumEngine:
 
     # ------------------------------------------------------------------ weight packing
     def pack(self, state_dict: Dict[str, torch.Tensor]):
-        sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
+        # BN folding and operand packing run on the HOST in float64 (a few ms for 3.3 M parameters); only the
+        # finished operands are uploaded.  (Folding on the device cost ~900 tiny torch launches per pack.)
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
         dev, f32 = self.device, torch.float32
+        cpu = torch.device("cpu")
         self.pn = []
         self.layers: List[_ConvLayer] = []
         self._plans.clear()
@@ -128,12 +138,12 @@ class FrustumEngine:
                 w = sd["%s.conv%d.0.weight" % (p, j)].double()[:, :, 0, 0]      # (Co,Ci)
                 s, sh = _fold_bn(sd, "%s.conv%d.1" % (p, j))
                 wf = (w * s[:, None]).to(f32)                                   # (Co,Ci) folded
-                lay["w%dt" % j] = wf.t().contiguous()                           # (Ci,Co)
-                lay["b%d" % j] = sh.to(f32).contiguous()
+                lay["w%dt" % j] = wf.t().contiguous().to(dev)                   # (Ci,Co)
+                lay["b%d" % j] = sh.to(f32).contiguous().to(dev)
                 if self.precision == 1 and j >= 2:
-                    lay["w%d_tc" % j] = pack_sw128(wf, min(c2, 128) if j == 2 else 128)
+                    lay["w%d_tc" % j] = pack_sw128(wf, min(c2, 128) if j == 2 else 128).to(dev)
                     if self.pn_cluster and c1 >= 256:    # 2-CTA variant: one C2-wide / 256-wide tile per K block
-                        lay["w%d_tc2" % j] = pack_sw128(wf, c2 if j == 2 else 256)
+                        lay["w%d_tc2" % j] = pack_sw128(wf, c2 if j == 2 else 256).to(dev)
             self.pn.append(lay)
         S, V = self.arch.num_scales, self.num_vec
         widths = (128, 256, 512, 512)[: S - 1]
@@ -147,39 +157,39 @@ class FrustumEngine:
             w = sd["conv_net.%s.0.weight" % name].double()                      # (Co,Ci,3)
             s, sh = _fold_bn(sd, "conv_net.%s.1" % name)
             cp, ncols = padded(ci), _round_up(co, 64)
-            wt = torch.zeros(3 * cp, ncols, dtype=torch.float64, device=dev)
+            wt = torch.zeros(3 * cp, ncols, dtype=torch.float64, device=cpu)
             for j in range(3):
                 wt[j * cp: j * cp + ci, :co] = (w[:, :, j] * s[:, None]).t()
-            bias = torch.zeros(ncols, dtype=torch.float64, device=dev)
+            bias = torch.zeros(ncols, dtype=torch.float64, device=cpu)
             bias[:co] = sh
             segs = [(src, ci, j - 1, stride) for j in range(3)]
             self.layers.append(_ConvLayer(name, segs, 3 * cp, ncols, co, 1, 1, wt.to(f32).contiguous(),
-                                          bias.to(f32).contiguous(), out, 0))
+                                          bias.to(f32).contiguous(), out, 0, dev))
 
         def merge(name, src_a, ca, src_b, cb, co, out):
             w = sd["conv_net.%s.0.weight" % name].double()[:, :, 0]            # (Co, ca+cb)
             s, sh = _fold_bn(sd, "conv_net.%s.1" % name)
             pa, pb, ncols = padded(ca), padded(cb), _round_up(co, 64)
-            wt = torch.zeros(pa + pb, ncols, dtype=torch.float64, device=dev)
+            wt = torch.zeros(pa + pb, ncols, dtype=torch.float64, device=cpu)
             wt[:ca, :co] = (w[:, :ca] * s[:, None]).t()
             wt[pa: pa + cb, :co] = (w[:, ca:] * s[:, None]).t()
-            bias = torch.zeros(ncols, dtype=torch.float64, device=dev)
+            bias = torch.zeros(ncols, dtype=torch.float64, device=cpu)
             bias[:co] = sh
             segs = [(src_a, ca, 0, 1), (src_b, cb, 0, 1)]
             self.layers.append(_ConvLayer(name, segs, pa + pb, ncols, co, 1, 1, wt.to(f32).contiguous(),
-                                          bias.to(f32).contiguous(), out, 0))
+                                          bias.to(f32).contiguous(), out, 0, dev))
 
         def deconv(name, src, ci, co, k, c_off):
             w = sd["conv_net.%s.0.weight" % name].double()                      # (Ci,Co,k)
             s, sh = _fold_bn(sd, "conv_net.%s.1" % name)
             ncols = _round_up(k * co, 64)
-            wt = torch.zeros(padded(ci), ncols, dtype=torch.float64, device=dev)
-            bias = torch.zeros(ncols, dtype=torch.float64, device=dev)
+            wt = torch.zeros(padded(ci), ncols, dtype=torch.float64, device=cpu)
+            bias = torch.zeros(ncols, dtype=torch.float64, device=cpu)
             for j in range(k):
                 wt[:ci, j * co:(j + 1) * co] = w[:, :, j] * s[None, :]
                 bias[j * co:(j + 1) * co] = sh
             self.layers.append(_ConvLayer(name, [(src, ci, 0, 1)], padded(ci), ncols, co, k, 1,
-                                          wt.to(f32).contiguous(), bias.to(f32).contiguous(), "cat", c_off))
+                                          wt.to(f32).contiguous(), bias.to(f32).contiguous(), "cat", c_off, dev))
 
         conv3("block1_conv1", "feat1", self.c3[0] + V, self.arch.block1_out, 1, "x1")
         prev, prev_c = "x1", self.arch.block1_out
@@ -195,14 +205,14 @@ class FrustumEngine:
             return
         # heads: columns [cls0, cls1, reg...] zero-padded to ld_logit (det_base.py:250-251,367-368)
         cin = self.arch.reg_in
-        wt = torch.zeros(_round_up(cin, 32), self.ld_logit, dtype=torch.float32, device=dev)
-        bias = torch.zeros(self.ld_logit, dtype=torch.float32, device=dev)
+        wt = torch.zeros(_round_up(cin, 32), self.ld_logit, dtype=torch.float32, device=cpu)
+        bias = torch.zeros(self.ld_logit, dtype=torch.float32, device=cpu)
         wt[:cin, 0:2] = sd["cls_out.weight"][:, :, 0].t()
         wt[:cin, 2:2 + self.out_size] = sd["reg_out.weight"][:, :, 0].t()
         bias[0:2] = sd["cls_out.bias"]
         bias[2:2 + self.out_size] = sd["reg_out.bias"]
         self.layers.append(_ConvLayer("heads", [("cat", cin, 0, 1)], _round_up(cin, 32), self.ld_logit,
-                                      self.ld_logit, 1, 0, wt.contiguous(), bias.contiguous(), "logits", 0))
+                                      self.ld_logit, 1, 0, wt.contiguous(), bias.contiguous(), "logits", 0, dev))
 
     # ------------------------------------------------------------------ shape plans
     def plan(self, B: int, N: int, T: Sequence[int]) -> "_Plan":
@@ -210,10 +220,12 @@ class FrustumEngine:
         (``with torch.cuda.stream(s): model(x)``) get disjoint workspaces/graphs and may overlap."""
         shape = (int(B), int(N), tuple(int(t) for t in T))
         key = shape + (torch.cuda.current_stream(self.device).cuda_stream,)
-        p = self._plans.get(key)
+        p = self._plans.pop(key, None)
         if p is None:
+            if len(self._plans) >= self.max_plans:       # LRU eviction (dict order = recency of use)
+                self._plans.pop(next(iter(self._plans)))
             p = _Plan(self, *shape)
-            self._plans[key] = p
+        self._plans[key] = p
         return p
 
     # ------------------------------------------------------------------ public calls
@@ -342,6 +354,7 @@ class _Plan:
             g.idx_scratch[s] = _ptr(self.idx32[s])
             g.feat_pitch[s] = self.P[s]
         g.ntiles = _ptr(self.ntiles)
+        g.force_scan = 1 if eng.group_scan else 0
         self.group_args = g
         self.pn_args = []
         for s in range(S if eng.has_feat else 0):

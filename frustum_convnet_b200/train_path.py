@@ -7,9 +7,8 @@ grouping runs on libfrustum_b200 (``QueryDepthPoint``) and the differentiable ar
 composed from torch CUDA ops on the modules' own parameters.  Loss definitions follow
 det_base.py:280-332,414-476, models/model_util.py:9-19,48-72, models/common.py:80-94,217-232 and
 models/box_transform.py:15-65.  The CPU Boost IoU metric (det_base.py:494-503,
-ops/pybind11/box_ops.h) is the "next" row 8(f)-1: with ``model.gpu_iou_metrics = True`` it is
-computed on the device by ``fcn_rbbox_iou_3d_pair`` (box_iou.py); the default still reports NaN
-until that kernel has had its GPU parity run.
+ops/pybind11/box_ops.h) is row 8(f)-1: it is computed on the device by ``fcn_rbbox_iou_3d_pair``
+(box_iou.py) by default; ``model.gpu_iou_metrics = False`` opts out (NaN placeholders).
 """
 from __future__ import annotations
 
@@ -130,6 +129,13 @@ def slice_output(out, num_bins, num_sizes):
             out[:, c1:c2].contiguous(), out[:, c2:].contiguous().view(n, num_sizes, 3))
 
 
+def _iou_metrics(c_metric, c_gt, thresh):
+    """(mean IoU_2D, mean IoU_3D, fraction >= thresh) on the device (det_base.py:494-503)."""
+    from .box_iou import rbbox_iou_3d_pair
+    _, stats = rbbox_iou_3d_pair(c_metric, c_gt, iou_thresh=thresh)
+    return stats
+
+
 def pointnet_det_torch(model, data):
     cfg = get_cfg()
     pc = data.get("point_cloud")
@@ -205,15 +211,13 @@ def pointnet_det_torch(model, data):
         cls_prec = accuracy(cls_probs, cls_label.view(-1), ignore=-1)
         head_prec = accuracy(h_pr, h_cls.view(-1))
         size_prec = accuracy(s_pr, size_class.view(-1))
-        if getattr(model, "gpu_iou_metrics", False):
+        if getattr(model, "gpu_iou_metrics", True):
             # det_base.py:488-500 with the boxes kept on the device (fcn_rbbox_iou_3d_pair instead of the
             # CPU Boost call on `.cpu().numpy()` copies): PREDICTED class labels, as the reference
-            from .box_iou import rbbox_iou_3d_pair
             h_lab, s_lab = torch.argmax(h_pr, -1), torch.argmax(s_pr, -1)
             c_metric = box_corners(center_preds, angle_decode(h_res, h_lab, nb), size_decode(s_res, mean_size, s_lab))
-            _, (iou2d, iou3d, iou3d_gt) = rbbox_iou_3d_pair(c_metric, c_gt, iou_thresh=cfg.IOU_THRESH)
-            iou2d, iou3d, iou3d_gt = (v.type_as(cls_prec) for v in (iou2d, iou3d, iou3d_gt))
-        else:   # opt-in until the kernel has had its GPU parity run
+            iou2d, iou3d, iou3d_gt = (v.type_as(cls_prec) for v in _iou_metrics(c_metric, c_gt, cfg.IOU_THRESH))
+        else:   # explicit opt-out (model.gpu_iou_metrics = False): NaN placeholders, no kernel launch
             iou2d = iou3d = iou3d_gt = torch.tensor(float("nan")).type_as(cls_prec)
     losses = {"total_loss": loss, "cls_loss": cls_loss, "center_loss": center_loss,
               "head_cls_loss": head_cls_loss, "head_res_loss": head_res_loss,

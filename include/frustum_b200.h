@@ -91,6 +91,7 @@ typedef struct {
     int32_t *idx_scratch[FCN_MAX_SCALES];   /* (B,T_s,K_s) int32: first min(hits,K) point indices */
     int feat_pitch[FCN_MAX_SCALES];         /* rows per frustum of feat[s] (>= T_s; 0 means T_s) */
     int32_t *ntiles;                        /* int32[FCN_MAX_SCALES] */
+    int force_scan;                         /* 1: section-scan kernel pair instead of the bit-matrix kernel (A/B) */
 } fcn_group_args;
 FCN_API int fcn_group_rows(const fcn_group_args *args, fcn_stream_t stream);
 

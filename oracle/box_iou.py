@@ -16,6 +16,15 @@ system dependency, absent from /root/reference and from this image).  This file 
 algorithm for two CONVEX polygons (Sutherland-Hodgman clipping + shoelace area; the union of two overlapping
 convex polygons is one polygon of area a + b - inter) in float64 and is cross-checked in
 tests/test_box_iou_cpu.py against closed-form cases and an independent point-sampling estimate.
+
+DEGENERATE RINGS (decision of round 2, pinned by tests/test_box_iou_cpu.py::test_degenerate_boxes): the reference
+appends the four BEV corners without `bg::correct` (box_ops.h:206-224).  A decoded box with exactly ONE negative
+footprint size (size_decode of untrained weights can produce it) gives a counter-clockwise ring, i.e. a polygon
+that violates Boost's concept (clockwise, closed); `bg::intersection`/`bg::union_` are unspecified on such
+input, so there is no reference value to match.  Such a pair scores (0, 0) here and in csrc/box_iou.cuh: an
+invalid box gets no overlap credit, and 0 <= IoU_3D <= IoU_2D <= 1 holds for every input.  Two negative
+footprint sizes are a valid box rotated by pi (orientation preserved); a negative HEIGHT needs no special
+case (`vol = max(0, area*h)`, `max(0, ymax - ymin)` already give IoU_3D = 0 with the reference's own formulas).
 """
 import numpy as np
 
@@ -62,11 +71,13 @@ def rbbox_iou_3d_pair(box_corners, qbox_corners):
     for n in range(N):
         poly = c[n][list(BEV_ORDER)][:, [0, 2]]
         qpoly = q[n][list(BEV_ORDER)][:, [0, 2]]
+        area, qarea = -_shoelace_ccw(poly), -_shoelace_ccw(qpoly)   # Boost: clockwise positive
+        if not (area > 0.0 and qarea > 0.0):
+            continue   # DEGENERATE RING (see the header): pinned decision, the pair scores (0, 0)
         inter = _clip_convex(poly, qpoly)
         inter_area = abs(_shoelace_ccw(inter)) if len(inter) >= 3 else 0.0
         if inter_area <= 0.0:
             continue
-        area, qarea = -_shoelace_ccw(poly), -_shoelace_ccw(qpoly)   # Boost: clockwise positive
         union_area = area + qarea - inter_area
         ymax = min(c[n, 0, 1], q[n, 0, 1])
         ymin = max(c[n, 4, 1], q[n, 4, 1])

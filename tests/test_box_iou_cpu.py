@@ -118,3 +118,51 @@ def test_device_arithmetic_compiled_for_the_host_matches_oracle(tmp_path):
     assert np.abs(out[ok] - want[ok]).max() <= 2e-5, np.abs(out[ok] - want[ok]).max()
     assert out[256].tolist() == pytest.approx([1.0, 1.0], abs=1e-6)
     assert not out[258].any() and not out[259].any()
+
+
+def _host_iou(tmp_path, pr, gt):
+    hdr = os.path.join(ROOT, "frustum_convnet_b200", "csrc", "box_iou.cuh")
+    src = tmp_path / "harness2.cpp"
+    src.write_text(HARNESS % hdr)
+    so = tmp_path / "libiou_host2.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-ffp-contract=off", "-o", str(so), str(src)])
+    lib = ctypes.CDLL(str(so))
+    pr = np.ascontiguousarray(pr, dtype=np.float32)
+    gt = np.ascontiguousarray(gt, dtype=np.float32)
+    out = np.full((pr.shape[0], 2), -1.0, dtype=np.float32)
+    P = ctypes.c_void_p
+    lib.host_rbbox_iou(ctypes.c_int(pr.shape[0]), P(pr.ctypes.data), P(gt.ctypes.data), P(out.ctypes.data))
+    return out
+
+
+def test_degenerate_boxes(tmp_path):
+    """Decoded boxes with negative sizes (untrained weights; the round-1 GPU failure): the pinned decision of
+    oracle/box_iou.py - a counter-clockwise (invalid) BEV ring scores (0, 0); two negative footprint sizes are
+    a valid box rotated by pi; a negative height gives IoU_3D = 0 through the reference's own max(0, .) terms -
+    and the invariants 0 <= IoU_3D <= IoU_2D <= 1 on random decoded boxes, for oracle AND device arithmetic."""
+    ctr, head = [[0.3, 0.1, 8.0]], [0.2]
+    gt = _boxes(ctr, head, [[3.9, 1.6, 1.5]])
+    good = ob.rbbox_iou_3d_pair(_boxes(ctr, head, [[3.9, 1.6, 1.5]]), gt)[0]
+    assert np.allclose(good, [1.0, 1.0])
+    for sz in ([-3.9, 1.6, 1.5], [3.9, -1.6, 1.5]):                       # one negative footprint size
+        assert not ob.rbbox_iou_3d_pair(_boxes(ctr, head, [sz]), gt).any()
+        assert not ob.rbbox_iou_3d_pair(gt, _boxes(ctr, head, [sz])).any()
+    both = ob.rbbox_iou_3d_pair(_boxes(ctr, head, [[-3.9, -1.6, 1.5]]), gt)[0]
+    assert np.allclose(both, [1.0, 1.0])                                  # rotated by pi: the same box
+    negh = ob.rbbox_iou_3d_pair(_boxes(ctr, head, [[3.9, 1.6, -1.5]]), gt)[0]
+    assert negh[0] == pytest.approx(1.0) and negh[1] == 0.0
+    rng = np.random.default_rng(11)
+    M = 512
+    c = rng.normal(0, 0.5, (M, 3)) + [0, 0, 8.0]
+    h = rng.uniform(-np.pi, np.pi, M)
+    s = rng.normal(0.5, 2.0, (M, 3))                                      # ~40 % negative entries
+    pr = _boxes(c, h, s)
+    gtb = _boxes(np.tile([[0.0, 0.0, 8.0]], (M, 1)), np.zeros(M), np.tile([[3.9, 1.6, 1.5]], (M, 1)))
+    want = ob.rbbox_iou_3d_pair(pr, gtb)
+    bad = (s[:, 0] * s[:, 1]) <= 0
+    assert bad.sum() > 50 and not want[bad].any()
+    assert ((want >= 0) & (want <= 1 + 1e-9)).all() and (want[:, 1] <= want[:, 0] + 1e-9).all()
+    got = _host_iou(tmp_path, pr, gtb)
+    assert np.isfinite(got).all() and np.abs(got - want).max() <= 5e-5
+    assert not got[bad].any()
+    assert ((got >= 0) & (got <= 1 + 1e-5)).all() and (got[:, 1] <= got[:, 0] + 1e-5).all()

@@ -33,11 +33,17 @@ def cuda_data(data):
     return {k: torch.from_numpy(v).to(dev()) for k, v in data.items()}
 
 
-def build_model(w, sd, workload_cfg):
+def build_model(w, sd, workload_cfg, precision=0, graph=False):
+    """precision / graph are set explicitly: the drop-in default is the benchmarked configuration
+    (TF32 + CUDA graph, FCN_PRECISION / FCN_CUDA_GRAPH), these tests pin each arithmetic separately."""
     modname = "det_base_sunrgbd" if w["arch"].num_scales == 5 else "det_base"
     mod = __import__("frustum_convnet_b200." + modname, fromlist=["PointNetDet"])
     m = mod.PointNetDet(3, num_vec=w["num_vec"])
     m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    for sub in m.modules():
+        if hasattr(sub, "resolved_precision"):
+            sub.precision = precision
+    m.use_cuda_graph = graph
     return m.to(dev()).eval()
 
 

@@ -63,9 +63,13 @@ def test_iou_edge_cases_and_scale():
     assert abs(float(m2) - want[:, 0].mean()) <= TOL and abs(float(m3) - want[:, 1].mean()) <= TOL
 
 
-def test_train_branch_reports_device_iou_metrics_when_enabled():
+def test_train_branch_reports_device_iou_metrics_by_default():
+    """The reference's train driver consumes IoU_<thresh> for best-model selection (train_net_det.py:203,378):
+    the device metric is the default; untrained weights decode negative sizes -> degenerate pairs score 0."""
     from frustum_convnet_b200 import config, synth
     from frustum_convnet_b200.det_base import PointNetDet
+    from frustum_convnet_b200 import train_path
+    from oracle import box_iou as ob
     cfg, w = config.load_workload("refine_car")
     sd = synth.make_state_dict(w["arch"], 3, "KITTI", seed=11)
     m = PointNetDet(3, num_vec=3)
@@ -73,10 +77,43 @@ def test_train_branch_reports_device_iou_metrics_when_enabled():
     m = m.cuda().train()
     data = {k: torch.from_numpy(v).cuda()
             for k, v in synth.make_frustums("refine_car", 4, seed=206, with_labels=True).items()}
-    _, off = m(data)
-    assert all(torch.isnan(off[k]) for k in ("IoU_2D", "IoU_3D", "IoU_" + str(cfg.IOU_THRESH)))
-    m.gpu_iou_metrics = True
-    losses, on = m(data)
+    captured = {}
+    orig = train_path._iou_metrics
+
+    def spy(c_metric, c_gt, thresh):
+        captured["pr"], captured["gt"] = c_metric.detach().cpu().numpy(), c_gt.detach().cpu().numpy()
+        return orig(c_metric, c_gt, thresh)
+
+    train_path._iou_metrics = spy
+    try:
+        losses, on = m(data)
+    finally:
+        train_path._iou_metrics = orig
     i2, i3, ig = (float(on[k]) for k in ("IoU_2D", "IoU_3D", "IoU_" + str(cfg.IOU_THRESH)))
     assert 0.0 <= i3 <= i2 + 1e-6 and i2 <= 1.0 + 1e-6 and 0.0 <= ig <= 1.0
     assert torch.isfinite(losses["total_loss"])
+    want = ob.rbbox_iou_3d_pair(captured["pr"], captured["gt"])          # same boxes through the oracle
+    assert abs(i2 - want[:, 0].mean()) <= TOL and abs(i3 - want[:, 1].mean()) <= TOL
+    m.gpu_iou_metrics = False                                            # explicit opt-out -> NaN placeholders
+    _, off = m(data)
+    assert all(torch.isnan(off[k]) for k in ("IoU_2D", "IoU_3D", "IoU_" + str(cfg.IOU_THRESH)))
+
+
+def test_iou_degenerate_predictions_on_device():
+    """Negative decoded sizes (counter-clockwise BEV ring) score (0, 0); invariants hold on random decoded boxes."""
+    from frustum_convnet_b200.box_iou import rbbox_iou_3d_pair
+    from oracle import box_iou as ob
+    rng = np.random.default_rng(11)
+    M = 2048
+    c = rng.normal(0, 0.5, (M, 3)) + [0, 0, 8.0]
+    h = rng.uniform(-np.pi, np.pi, M)
+    s = rng.normal(0.5, 2.0, (M, 3))
+    pr = ob.box3d_corners(c, h, s).astype(np.float32)
+    gt = ob.box3d_corners(np.tile([[0.0, 0.0, 8.0]], (M, 1)), np.zeros(M),
+                          np.tile([[3.9, 1.6, 1.5]], (M, 1))).astype(np.float32)
+    got = rbbox_iou_3d_pair(torch.from_numpy(pr).cuda(), torch.from_numpy(gt).cuda()).cpu().numpy()
+    want = ob.rbbox_iou_3d_pair(pr, gt)
+    assert np.isfinite(got).all() and np.abs(got - want).max() <= TOL
+    bad = (s[:, 0] * s[:, 1]) <= 0
+    assert not got[bad].any()
+    assert ((got >= 0) & (got <= 1 + 1e-5)).all() and (got[:, 1] <= got[:, 0] + 1e-5).all()
