@@ -98,8 +98,7 @@ class ClockSampler:
             self.proc = None
 
     def sample_now(self):
-        """One synchronous sample (called from the issuing thread in the middle of a timed loop, so that short
-        regions are covered even if the polling thread is starved of the GIL)."""
+        """One NVML sample (called by the polling thread)."""
         nv = self.nvml
         if nv is None:
             return
@@ -116,9 +115,11 @@ class ClockSampler:
             pass
 
     def _poll(self):
+        # background polling only: NVML calls go through ctypes (GIL released), 2 ms period - no NVML call is
+        # ever made from the issuing thread inside a timed region
         while self.run:
             self.sample_now()
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -245,7 +246,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, args.batch),
+        "config": {"workload": workload_name(args.workload, args.batch) +
+                               " [CPU arm: bounded sample of %d frustums per step]" % sample_B,
                    "batch_per_gpu": args.batch, "global_batch": args.batch, "parallelism": "dp1",
                    "reference_sample": "%d frustums per step (bounded CPU sample of the same workload)" % sample_B},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": n, "kind": "port",
@@ -272,6 +274,9 @@ def main():
                     help="points per frustum (default: the workload's yaml value; e.g. people at 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-group", type=int, default=1, help="N>1: steps covered by one result all-gather")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="device time to accumulate per mode by repeating the K-step region (median reported)")
+    ap.add_argument("--max-regions", type=int, default=400)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "8")),
                     help="forwards in flight: steps are issued round-robin on this many CUDA streams")
     args = ap.parse_args()
@@ -401,39 +406,85 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- timed region: inputs resident in HBM
-    # untimed pre-warm: graph capture + clock ramp; a FIXED step count without collectives so that all
-    # ranks issue identical NCCL sequences afterwards
+    # ---- e2e step: public API with HOST (pinned) buffers, H2D + D2H inside the timed region
+    host_outs = [torch.empty(pl.out_flat.shape, dtype=torch.float32).pin_memory() for pl in plans]
+    d2h_bytes = int(host_outs[0].numel() * 4)
+    in_views = [pl.input_views() for pl in plans]
+
+    def step_e2e(i, comm=True, last=False):
+        k = i % nstream
+        with torch.cuda.stream(streams[k]):
+            if world > 1 and gather_done[k // G] is not None:
+                streams[k].wait_event(gather_done[k // G])
+            plans[k].in_flat.copy_(host_pool[i % npool], non_blocking=True)    # H2D of this step's inputs
+            model(in_views[k])                                                 # public API, zero-copy staging
+            host_outs[k].copy_(plans[k].out_flat, non_blocking=True)           # D2H of the 6-tuple block
+        if world > 1 and comm and not no_comm:
+            after_step(i, last)
+
+    # ---- untimed pre-warm: graph capture + clock ramp (a FIXED step count without collectives, so that all
+    # ranks issue identical NCCL sequences afterwards), then both step kinds WITH their collectives: NCCL's
+    # lazy channel/proxy setup must not land in a timed region (>= 64 gathers before the first one)
     for j in range(512):
         step_resident(j, comm=False)
         if j % 64 == 63:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
-    for i in range(args.warmup):
-        step_resident(i, last=(i == args.warmup - 1))
+    nwarm = max(args.warmup, 64 if world > 1 else args.warmup)
+    for i in range(nwarm):
+        step_resident(i, last=(i == nwarm - 1))
+    for i in range(nwarm):
+        step_e2e(i, last=(i == nwarm - 1))
     barrier()
+
+    # ---- timed regions.  ONE region = EXACTLY `--steps` steps between two CUDA events, barrier + synchronize on
+    # both sides.  A 20-step region lasts only ~3 ms, so the region is REPEATED R times (R chosen so that each
+    # mode accumulates >= ~0.5 s of device time, bounded) and the MEDIAN region is reported; resident and e2e
+    # regions ALTERNATE, so both medians see the same clocks / thermal state.  Per region the max over ranks is
+    # taken (one all-reduce over the vector of region times after the loop).
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    counters = {"res": 0, "e2e": 0}
+
+    def region(kind):
+        fn = step_resident if kind == "res" else step_e2e
+        base = args.warmup + counters[kind]
+        counters[kind] += args.steps
+        barrier()
+        e0.record()
+        fork_streams()
+        for i in range(args.steps):
+            fn(base + i, last=(i == args.steps - 1))
+        join_streams()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    pilot = torch.tensor([region("res"), region("e2e")], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pilot, op=dist.ReduceOp.MAX)
+    R = int(min(max(np.ceil(args.min_seconds * 1e3 / max(float(pilot.min().item()), 1e-3)), 3), args.max_regions))
     sampler = ClockSampler(local_rank)
-    sample_at = {args.steps // 4, args.steps // 2, (3 * args.steps) // 4}
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    fork_streams()
-    for i in range(args.steps):
-        step_resident(args.warmup + i, last=(i == args.steps - 1))
-        if rank == 0 and i in sample_at:
-            sampler.sample_now()
-    join_streams()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    t_regions = torch.zeros((2, R), dtype=torch.float64)
+    for r in range(R):
+        t_regions[0, r] = region("res")
+        t_regions[1, r] = region("e2e")
+    clocks = sampler.stop() if rank == 0 else None    # samples cover all timed regions (resident + e2e)
+    t_regions = t_regions.to(dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+        dist.all_reduce(t_regions, op=dist.ReduceOp.MAX)
+    t_regions = t_regions.cpu().numpy()
+    ms_total = float(np.median(t_regions[0]))
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
+    e2e_ms_step = float(np.median(t_regions[1])) / args.steps
+    e2e_value = world * B / (e2e_ms_step * 1e-3)
+    spread = {"regions": R, "steps_per_region": args.steps,
+              "resident_ms_per_step_p10_p50_p90": [float(np.percentile(t_regions[0], q)) / args.steps for q in (10, 50, 90)],
+              "e2e_ms_per_step_p10_p50_p90": [float(np.percentile(t_regions[1], q)) / args.steps for q in (10, 50, 90)],
+              "device_seconds_timed": float(t_regions.sum() * 1e-3),
+              "e2e_le_value": bool(e2e_value <= value * 1.02)}
 
     # host-side issue cost per step (queue empty, no waiting on the GPU): shows whether the loop is CPU-bound
     torch.cuda.synchronize()
@@ -442,41 +493,6 @@ def main():
         step_resident(i, comm=False)
     host_us = (time.perf_counter() - t_h) / 32 * 1e6
     torch.cuda.synchronize()
-
-    # ---- e2e: public API with HOST (pinned) buffers, H2D + D2H inside the timed region
-    host_outs = [torch.empty(pl.out_flat.shape, dtype=torch.float32).pin_memory() for pl in plans]
-    d2h_bytes = int(host_outs[0].numel() * 4)
-
-    in_views = [pl.input_views() for pl in plans]
-
-    def step_e2e(i, last=False):
-        k = i % nstream
-        with torch.cuda.stream(streams[k]):
-            if world > 1 and gather_done[k // G] is not None:
-                streams[k].wait_event(gather_done[k // G])
-            plans[k].in_flat.copy_(host_pool[i % npool], non_blocking=True)    # H2D of this step's inputs
-            model(in_views[k])                                                 # public API, zero-copy staging
-            host_outs[k].copy_(plans[k].out_flat, non_blocking=True)           # D2H of the 6-tuple block
-        if world > 1 and not no_comm:
-            after_step(i, last)
-
-    for i in range(args.warmup):
-        step_e2e(i, last=(i == args.warmup - 1))
-    barrier()
-    e0.record()
-    fork_streams()
-    for i in range(args.steps):
-        step_e2e(args.warmup + i, last=(i == args.steps - 1))
-        if rank == 0 and i in sample_at:
-            sampler.sample_now()
-    join_streams()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B / (float(t.item()) / args.steps * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None    # samples cover both timed regions (resident + e2e)
 
     # ---- per-kernel timing of the eager launch sequence (CUDA events on the launching stream)
     kt = plan.time_kernels(dev_pool, iters=20) if rank == 0 else None
@@ -538,12 +554,13 @@ def main():
             "l2": "inputs cycle through a %d-batch pool (%.0f MB > 126 MB L2); weights/workspaces stay L2-resident"
                   % (npool, npool * step_in_bytes / 1e6),
             "cuda_graph": True, "precision": roofline["precision"], "streams_in_flight": nstream,
+            "timing": "median of %d repeated %d-step regions (resident and e2e regions alternate)" % (spread["regions"], args.steps),
             "collective": ("none (single GPU)" if world == 1 else
                            "NCCL all_gather of the per-rank result blocks, one per %d steps (%d issued in this run)"
                            % (G, n_gathers[0]))},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(plan.in_flat.numel() * 4),
                 "d2h_bytes_per_step": d2h_bytes},
-        "host_issue_us_per_step": host_us, "latency": latency,
+        "host_issue_us_per_step": host_us, "latency": latency, "timing": spread,
         "gpu_launches": kt["launches_per_step"] * args.steps,
         "launches_per_step": kt["launches_per_step"],
         "roofline": roofline, "hbm": hbm, "clocks": clocks,

@@ -566,18 +566,27 @@ class _Plan:
         return self._views(self.out_flat.clone()) if copy_out else out
 
     def _run(self, pc, centers, one_hot, use_graph=False):
-        self._check_inputs(pc, centers, one_hot)
-        with torch.cuda.device(self.eng.device):
-            if not use_graph:
-                self._launch_feat(pc, centers, one_hot)
-                self._launch_fcn()
-                self._launch_decode(centers[1])
-                return self.out
-            self._stage(pc, centers, one_hot)
-            if self.graph is None:
-                self._capture()
-            self.graph.replay()
+        own = use_graph and pc.data_ptr() == self.in_flat.data_ptr()   # the plan's own input views: valid by construction
+        if not own:
+            self._check_inputs(pc, centers, one_hot)
+        dev = self.eng.device
+        if dev.index is not None and torch.cuda.current_device() != dev.index:
+            with torch.cuda.device(dev):
+                return self._run_on_device(pc, centers, one_hot, use_graph, own)
+        return self._run_on_device(pc, centers, one_hot, use_graph, own)
+
+    def _run_on_device(self, pc, centers, one_hot, use_graph, own):
+        if not use_graph:
+            self._launch_feat(pc, centers, one_hot)
+            self._launch_fcn()
+            self._launch_decode(centers[1])
             return self.out
+        if not own:
+            self._stage(pc, centers, one_hot)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        return self.out
 
     def _capture(self):
         skip = set(os.environ.get("FCN_DIAG_SKIP", "").split(","))   # timing diagnostics only
