@@ -69,6 +69,50 @@ class ConvArgs(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+MEGA_MAX_DEPS = 4
+
+
+class DecodeOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("cls_probs", "center", "heading", "size", "heading_probs", "size_probs")]
+
+
+class MegaSeg(C.Structure):
+    _fields_ = [("map_idx", C.c_int), ("kblocks", C.c_int), ("tap", C.c_int), ("stride", C.c_int)]
+
+
+class MegaLayer(C.Structure):
+    _fields_ = [
+        ("n_seg", C.c_int), ("seg", MegaSeg * MAX_SEGS),
+        ("n_stage", C.c_int), ("NT", C.c_int), ("n_tiles_n", C.c_int),
+        ("relu", C.c_int), ("round_out", C.c_int), ("up", C.c_int), ("Cout", C.c_int),
+        ("P_m", C.c_int), ("T_out", C.c_int), ("n_rows", C.c_int),
+        ("ld_out", C.c_int), ("P_store", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int),
+        ("is_heads", C.c_int), ("flag_base", C.c_int),
+        ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+    ]
+
+
+class MegaDep(C.Structure):
+    _fields_ = [("first", C.c_int), ("count", C.c_int), ("target", C.c_int)]
+
+
+class MegaJob(C.Structure):
+    _fields_ = [("layer", C.c_int), ("m_tile", C.c_int), ("n_tile", C.c_int), ("n_dep", C.c_int),
+                ("dep", MegaDep * MEGA_MAX_DEPS)]
+
+
+class MegaArgs(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int), ("n_jobs", C.c_int), ("n_flags", C.c_int), ("grid", C.c_int),
+        ("layers", C.c_void_p), ("jobs", C.c_void_p), ("tmaps", C.c_void_p), ("sync", C.c_void_p),
+        ("B", C.c_int), ("T", C.c_int), ("NH", C.c_int), ("NS", C.c_int),
+        ("center_ref", C.c_void_p), ("mean_size", C.c_void_p),
+        ("n_out", C.c_int), ("n_flag_out", C.c_int),
+        ("outs", DecodeOut * MAX_PEERS), ("flag_out", C.c_void_p * MAX_PEERS),
+    ]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
 _I, _F, _P = C.c_int, C.c_float, C.c_void_p
 SIGNATURES = {
@@ -79,6 +123,7 @@ SIGNATURES = {
     "fcn_group_rows": (_I, [C.POINTER(GroupArgs), _P]),
     "fcn_pointnet_tiles": (_I, [C.POINTER(PointnetArgs), _P]),
     "fcn_conv_gemm": (_I, [C.POINTER(ConvArgs), _P]),
+    "fcn_mega_forward": (_I, [C.POINTER(MegaArgs), _P]),
     "fcn_decode_eval": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fcn_bct_to_btc": (_I, [_I, _I, _I, _I, _I, _P, _P, _P]),
     "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _I, _P, _P, _P]),

@@ -4,76 +4,20 @@
 // heading-bin and size-cluster scores, argmax, centre = offset + center_ref2) together with
 // angle_decode / size_decode of models/box_transform.py:28-41,5-12.  One thread per (b, t) row.
 #include "common.cuh"
+#include "decode.cuh"
 
 namespace fcn {
-
-constexpr int DEC_MAX_BINS = 64;
 
 __global__ void decode_eval_kernel(int B, int T, int pitch, int ld, int NH, int NS,
                                    const float *__restrict__ logits,
                                    const float *__restrict__ center_ref,
-                                   const float *__restrict__ mean_size, float *__restrict__ cls_probs,
-                                   float *__restrict__ center, float *__restrict__ heading,
-                                   float *__restrict__ size, float *__restrict__ heading_probs,
-                                   float *__restrict__ size_probs) {
+                                   const float *__restrict__ mean_size, DecodeOut out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_wait();
     pdl_launch_dependents();
     if (r >= B * T) return;
     const int b = r / T, t = r - b * T;
-    const float *row = logits + ((size_t)b * pitch + t) * ld;
-    // class softmax (det_base.py:378)
-    {
-        const float a = row[0], c = row[1];
-        const float m = fmaxf(a, c);
-        const float ea = expf(a - m), ec = expf(c - m);
-        const float s = ea + ec;
-        cls_probs[(size_t)r * 2 + 0] = ea / s;
-        cls_probs[(size_t)r * 2 + 1] = ec / s;
-    }
-    // centre = regressed offset + section centre (det_base.py:394)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        center[(size_t)r * 3 + c] = __fadd_rn(row[2 + c], __ldg(center_ref + ((size_t)b * 3 + c) * T + t));
-    const float *hs = row + 5, *hr = hs + NH, *ss = hr + NH, *sr = ss + NS;
-    // heading: softmax, argmax (first maximum), angle_decode (box_transform.py:28-41)
-    int hl = 0;
-    {
-        float m = hs[0];
-        for (int i = 1; i < NH; ++i) m = fmaxf(m, hs[i]);
-        float e[DEC_MAX_BINS], s = 0.f;
-        for (int i = 0; i < NH; ++i) { e[i] = expf(hs[i] - m); s += e[i]; }
-        float best = -1.f;
-        for (int i = 0; i < NH; ++i) {
-            const float pr = e[i] / s;
-            heading_probs[(size_t)r * NH + i] = pr;
-            if (pr > best) { best = pr; hl = i; }
-        }
-        const float apc = (float)(2.0 * 3.14159265358979323846 / (double)NH);
-        const float half = (float)(2.0 * 3.14159265358979323846 / (double)NH / 2.0);
-        float ang = __fadd_rn(__fmul_rn((float)hl, apc), __fmul_rn(hr[hl], half));
-        if (ang > (float)3.14159265358979323846) ang = __fsub_rn(ang, (float)(2.0 * 3.14159265358979323846));
-        heading[r] = ang;
-    }
-    // size: softmax, argmax, size_decode (box_transform.py:5-12)
-    {
-        float m = ss[0];
-        for (int i = 1; i < NS; ++i) m = fmaxf(m, ss[i]);
-        float e[DEC_MAX_BINS], s = 0.f;
-        for (int i = 0; i < NS; ++i) { e[i] = expf(ss[i] - m); s += e[i]; }
-        float best = -1.f;
-        int sl = 0;
-        for (int i = 0; i < NS; ++i) {
-            const float pr = e[i] / s;
-            size_probs[(size_t)r * NS + i] = pr;
-            if (pr > best) { best = pr; sl = i; }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float ex = __ldg(mean_size + sl * 3 + c);
-            size[(size_t)r * 3 + c] = __fadd_rn(__fmul_rn(sr[sl * 3 + c], ex), ex);
-        }
-    }
+    decode_row(logits + ((size_t)b * pitch + t) * ld, r, b, t, T, NH, NS, center_ref, mean_size, &out, 1);
 }
 
 // (B,C,T) -> (B,T,ld): pad channels [C,ld) are written as zero.
@@ -129,9 +73,9 @@ extern "C" int fcn_decode_eval(int B, int T, int pitch, int ld, int num_heading_
     FCN_REQUIRE(logits && center_ref && mean_size && cls_probs && center && heading && size &&
                     heading_probs && size_probs, "NULL pointer");
     const int n = B * T;
+    DecodeOut out = {cls_probs, center, heading, size, heading_probs, size_probs};
     FCN_CUDA(launch_pdl(decode_eval_kernel, dim3(ceil_div(n, 128)), dim3(128), (size_t)0, (cudaStream_t)stream,
-                        B, T, pitch, ld, num_heading_bin, num_size, logits, center_ref, mean_size, cls_probs,
-                        center, heading, size, heading_probs, size_probs));
+                        B, T, pitch, ld, num_heading_bin, num_size, logits, center_ref, mean_size, out));
     return FCN_OK;
 }
 

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import mega as _mega
 from .config import DATASET_INFO, ArchSpec
 from .synth import fcn_layer_table, reg_out_size
 
@@ -104,6 +105,10 @@ class FrustumEngine:
         # pointnet_s4; no gain at 128 channels (26.2 vs 27.0 us), so those stay on the 1-CTA kernel
         self.pn_cluster = os.environ.get("FCN_PN_CLUSTER", "1") == "1"
         self.group_scan = os.environ.get("FCN_GROUP_SCAN") is not None   # A/B: section-scan grouping kernels
+        # persistent FCN kernel (all conv layers + heads + decode in one launch, csrc/fcn_mega.cu); FCN_MEGA=0
+        # falls back to one fcn_conv_gemm launch per layer + fcn_decode_eval (kept as the A/B and module-API path)
+        self.use_mega = (self.precision == 1 and self.use_tma and os.environ.get("FCN_MEGA", "0") != "0")
+        self.mega_grid = int(os.environ.get("FCN_MEGA_GRID", "0"))       # persistent CTAs (0: one per SM)
         self.tile_rows = 64 if self.precision == 0 else 128
         self.out_size = reg_out_size(dataset, self.num_bins)
         self.ld_logit = _round_up(2 + self.out_size, 64)
@@ -417,6 +422,90 @@ class _Plan:
             a.P_store = out.shape[1]
             self.conv_args.append(a)
 
+        self.mega_args = None
+        if eng.use_mega and eng.has_heads and all(a.precision in (3, 4) for a in self.conv_args):
+            self._build_mega()
+
+    def mega_descs(self):
+        """Shape-level layer descriptions for the persistent FCN kernel (pure host arithmetic, testable on the CPU)."""
+        eng = self.eng
+        descs = []
+        for L in eng.layers:
+            src0, stride = L.segs[0][0], L.segs[0][3]
+            T_in, P_in = self.valid_T[src0], self.buf[src0].shape[1]
+            T_out = T_in if stride == 1 else (T_in + 1) // 2
+            P_m = P_in // stride
+            out = self.buf[L.out]
+            nt = 128 if L.n_cols % 128 == 0 else 64
+            descs.append(_mega.LayerDesc(L.name, L.segs, L.K_pad, L.n_cols, L.Cout, L.up, L.relu, L.out, L.c_off, nt,
+                                         1 if L.name != "heads" else 0, P_m, T_out, self.B * P_m, out.shape[2],
+                                         out.shape[1], self.valid_T[L.out]))
+        return descs
+
+    def _build_mega(self):
+        """Tables of the persistent FCN kernel (mega.py): tensor maps, layers, topologically ordered jobs."""
+        eng, dev = self.eng, self.eng.device
+        descs = self.mega_descs()
+        map_keys, rows, jobs, nflags = _mega.build_tables(descs)
+        maps = (C.c_ubyte * (128 * len(map_keys)))()
+        for i, (src, st) in enumerate(map_keys):
+            t = self.buf[src]
+            _lib.call("fcn_encode_activation_map", C.addressof(maps) + 128 * i, _ptr(t), 1, self.B * t.shape[1],
+                      t.shape[2], st)
+        ptrs = [(a.w_tc, a.bias, a.out) for a in self.conv_args]
+        LA, JA = _mega.to_ctypes(descs, rows, jobs, ptrs)
+
+        def upload(cobj):
+            return torch.frombuffer(bytearray(bytes(cobj)), dtype=torch.uint8).to(dev)
+
+        self._mega_dev = (upload(maps), upload(LA), upload(JA))
+        self.mega_sync = torch.zeros(4 + nflags, dtype=torch.int32, device=dev)
+        m = _lib.MegaArgs()
+        m.n_layers, m.n_jobs, m.n_flags, m.grid = len(descs), len(jobs), nflags, eng.mega_grid
+        m.tmaps, m.layers, m.jobs = (_ptr(self._mega_dev[0]), _ptr(self._mega_dev[1]), _ptr(self._mega_dev[2]))
+        m.sync = _ptr(self.mega_sync)
+        m.B, m.T, m.NH, m.NS = self.B, self.T[1], eng.num_bins, eng.num_size
+        m.center_ref, m.mean_size = _ptr(self.in_centers[1]), _ptr(eng.mean_size)
+        m.n_out, m.n_flag_out = 1, 0
+        self._set_decode_out(m.outs[0], self.out)
+        self.mega_args = m
+        self.mega_jobs = len(jobs)
+
+    @staticmethod
+    def _set_decode_out(slot, outs):
+        (slot.cls_probs, slot.center, slot.heading, slot.size, slot.heading_probs, slot.size_probs) = \
+            [_ptr(o) for o in outs]
+
+    def set_peer_outputs(self, peer_blocks, flag_ptrs=()):
+        """Multi-GPU result exchange without a collective: `peer_blocks` are flat fp32 blocks (this rank's slot
+        of every peer's gather buffer, mapped peer memory) with the layout of ``out_flat``; the heads epilogue
+        of the persistent FCN kernel stores the decoded rows into all of them over NVLink.  `flag_ptrs`: int32
+        device addresses that receive the forward's epoch number on completion."""
+        assert self.mega_args is not None, "peer outputs need the persistent FCN kernel (TF32 path)"
+        assert self.graph is None, "set peer outputs before the first graph capture"
+        m = self.mega_args
+        assert 1 + len(peer_blocks) <= _lib.MAX_PEERS and len(flag_ptrs) <= _lib.MAX_PEERS
+        self._peer_keepalive = list(peer_blocks)
+        for i, blk in enumerate(peer_blocks):
+            assert blk.dtype == torch.float32 and blk.numel() == self.out_flat.numel()
+            self._set_decode_out(m.outs[1 + i], self._views(blk))
+        m.n_out = 1 + len(peer_blocks)
+        for i, fp in enumerate(flag_ptrs):
+            m.flag_out[i] = fp
+        m.n_flag_out = len(flag_ptrs)
+
+    def _launch_mega(self, center_ref2):
+        self.mega_args.center_ref = _ptr(center_ref2)
+        _lib.call("fcn_mega_forward", C.byref(self.mega_args), _stream())
+
+    def _launch_tail(self, center_ref2):
+        """FCN + heads + decode: one persistent kernel, or (FCN_MEGA=0 / fp32) one launch per layer + decode."""
+        if self.mega_args is not None:
+            self._launch_mega(center_ref2)
+        else:
+            self._launch_fcn()
+            self._launch_decode(center_ref2)
+
     # ---- launch sequences (all asynchronous on the current stream)
     def _launch_feat(self, pc, centers, one_hot):
         g = self.group_args
@@ -578,8 +667,7 @@ class _Plan:
     def _run_on_device(self, pc, centers, one_hot, use_graph, own):
         if not use_graph:
             self._launch_feat(pc, centers, one_hot)
-            self._launch_fcn()
-            self._launch_decode(centers[1])
+            self._launch_tail(centers[1])
             return self.out
         if not own:
             self._stage(pc, centers, one_hot)
@@ -595,9 +683,7 @@ class _Plan:
             if "feat" not in skip:
                 self._launch_feat(self.in_pc, self.in_centers, self.in_onehot)
             if "fcn" not in skip:
-                self._launch_fcn()
-            if "decode" not in skip:
-                self._launch_decode(self.in_centers[1])
+                self._launch_tail(self.in_centers[1])
 
         seq()   # warm-up run outside capture (sets function attributes, loads modules)
         torch.cuda.current_stream().synchronize()
@@ -646,8 +732,9 @@ class _Plan:
         between two events (hot L2, no host launch overhead; includes the inter-kernel gap exactly
         like the whole-forward graph does).  Also returns executed/nominal FLOPs per launch."""
         eng, S = self.eng, self.eng.arch.num_scales
+        mega = self.mega_args is not None
         names = ["group_rows"] + ["pointnet_s%d" % (s + 1) for s in range(S)] + \
-            [L.name for L in eng.layers] + ["decode_eval"]
+            (["fcn_mega"] if mega else [L.name for L in eng.layers] + ["decode_eval"])
         d = dev_pool[0]
         self.in_pc.copy_(d["point_cloud"])
         for dst, i in zip(self.in_centers, range(S)):
@@ -664,8 +751,11 @@ class _Plan:
 
         calls = [call_group]
         calls += [(lambda a=a: _lib.call("fcn_pointnet_tiles", C.byref(a), _stream())) for a in self.pn_args]
-        calls += [(lambda a=a: _lib.call("fcn_conv_gemm", C.byref(a), _stream())) for a in self.conv_args]
-        calls += [lambda: self._launch_decode(self.in_centers[1])]
+        if mega:
+            calls += [lambda: self._launch_mega(self.in_centers[1])]
+        else:
+            calls += [(lambda a=a: _lib.call("fcn_conv_gemm", C.byref(a), _stream())) for a in self.conv_args]
+            calls += [lambda: self._launch_decode(self.in_centers[1])]
         acc = np.zeros(len(names))
         with torch.cuda.device(eng.device):
             for fn in calls:       # eager warm-up of the whole sequence (valid tiles/feats for later kernels)
@@ -695,12 +785,17 @@ class _Plan:
             mac = 3 * c1 + c1 * c2 + c2 * c3
             kern.append(dict(name="pointnet_s%d" % (s + 1), ms=float(acc[1 + s]),
                              executed_gflop=2e-9 * mac * rows_exec[s], nominal_gflop=2e-9 * mac * rows_nom[s]))
+        fcn_gf = []
         for j, (L, a) in enumerate(zip(eng.layers, self.conv_args)):
             kreal = sum(sg[1] for sg in L.segs)
             nreal = (2 + eng.out_size) if L.name == "heads" else L.up * L.Cout
-            gf = 2e-9 * a.B * a.T_out * kreal * nreal
-            kern.append(dict(name=L.name, ms=float(acc[1 + S + j]), executed_gflop=gf, nominal_gflop=gf))
-        kern.append(dict(name="decode_eval", ms=float(acc[-1]), executed_gflop=0.0, nominal_gflop=0.0))
+            fcn_gf.append(2e-9 * a.B * a.T_out * kreal * nreal)
+        if mega:
+            kern.append(dict(name="fcn_mega", ms=float(acc[1 + S]), executed_gflop=sum(fcn_gf), nominal_gflop=sum(fcn_gf)))
+        else:
+            for j, L in enumerate(eng.layers):
+                kern.append(dict(name=L.name, ms=float(acc[1 + S + j]), executed_gflop=fcn_gf[j], nominal_gflop=fcn_gf[j]))
+            kern.append(dict(name="decode_eval", ms=float(acc[-1]), executed_gflop=0.0, nominal_gflop=0.0))
         for k_ in kern:
             k_["executed_tflops"] = k_["executed_gflop"] / max(k_["ms"], 1e-9)  # GFLOP/ms == TFLOP/s
         return dict(kernels=kern, launches_per_step=len(names) + 1,   # group_rows = count + emit kernels

@@ -178,6 +178,62 @@ FCN_API int fcn_decode_eval(int B, int T, int pitch, int ld, int num_heading_bin
                     float *center, float *heading, float *size, float *heading_probs,
                     float *size_probs, fcn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (5b) Persistent FCN kernel: every fcn_conv_gemm layer of ConvFeatNet + heads (4) and the eval decode (5) of
+ *      one forward in ONE launch (models/det_base.py:196-224,367-411).  The host describes the network as
+ *        layers : per layer the A segments (tensor-map index, 32-channel blocks, kernel tap, stride), the
+ *                 packed TF32 weight image / bias, the output slice and the index of its completion counters;
+ *        jobs   : one [128 rows x NT columns] output tile each, in TOPOLOGICAL order (a job depends only on jobs
+ *                 with a smaller index), with the counters (first, count, target) it has to wait for;
+ *        tmaps  : DEVICE array of 128-byte tensor maps (fcn_encode_activation_map), 64-byte aligned;
+ *        sync   : DEVICE int32[4 + n_flags], zero-initialised ONCE by the caller; [0] job counter, [1] finished
+ *                 CTAs, [2] epoch (forwards completed), [4..] per-(layer,row-tile) completion counters.  The
+ *                 kernel resets [0],[1],[4..] itself at the end of every forward.
+ *      Persistent CTAs fetch jobs with an atomic counter (deadlock-free under any co-residency, see fcn_mega.cu).
+ *      The heads layer (is_heads) stores the logits row and decodes it in place into `n_out` output sets:
+ *      outs[0] is the local 6-tuple block, outs[1..] are peer buffers (mapped NVLink peer memory) - the
+ *      multi-GPU result exchange without a collective; flag_out[i] (may be NULL) receives the epoch number when
+ *      the forward is complete (system-scope release).
+ * ------------------------------------------------------------------------------------------ */
+#define FCN_MAX_PEERS 8
+#define FCN_MEGA_MAX_DEPS 4
+typedef struct {
+    float *cls_probs, *center, *heading, *size, *heading_probs, *size_probs;
+} fcn_decode_out;
+typedef struct {
+    int map_idx, kblocks, tap, stride;
+} fcn_mega_seg;
+typedef struct {
+    int n_seg;
+    fcn_mega_seg seg[FCN_MAX_SEGS];
+    int n_stage;                 /* K_pad / 64 */
+    int NT, n_tiles_n;           /* N tile (128 | 64) and their number */
+    int relu, round_out, up, Cout;
+    int P_m, T_out, n_rows;      /* GEMM row space: row r = b*P_m + t, valid iff t < T_out; n_rows = B*P_m */
+    int ld_out, P_store, T_store, c_off;
+    int is_heads, flag_base;
+    const void *w_tc;            /* packed stage images, N-tile major */
+    const float *bias;
+    float *out;
+} fcn_mega_layer;
+typedef struct {
+    int layer, m_tile, n_tile, n_dep;
+    struct { int first, count, target; } dep[FCN_MEGA_MAX_DEPS];
+} fcn_mega_job;
+typedef struct {
+    int n_layers, n_jobs, n_flags, grid;   /* grid: persistent CTAs (0 = one per SM) */
+    const fcn_mega_layer *layers;          /* device */
+    const fcn_mega_job *jobs;              /* device */
+    const void *tmaps;                     /* device */
+    int32_t *sync;                         /* device */
+    int B, T, NH, NS;                      /* decode: frustums, positions (T2), heading bins, size clusters */
+    const float *center_ref, *mean_size;
+    int n_out, n_flag_out;
+    fcn_decode_out outs[FCN_MAX_PEERS];
+    int32_t *flag_out[FCN_MAX_PEERS];
+} fcn_mega_args;
+FCN_API int fcn_mega_forward(const fcn_mega_args *args, fcn_stream_t stream);
+
 /* Layout helpers for the channel-first module APIs: (B,C,T) <-> (B,pitch >= T,ld) position-major. */
 FCN_API int fcn_bct_to_btc(int B, int C, int T, int pitch, int ld, const float *src, float *dst,
                            fcn_stream_t stream);
