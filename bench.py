@@ -273,7 +273,10 @@ def main():
     ap.add_argument("--points", type=int, default=None,
                     help="points per frustum (default: the workload's yaml value; e.g. people at 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-group", type=int, default=1, help="N>1: steps covered by one result all-gather")
+    ap.add_argument("--gather-group", type=int, default=1, help="N>1, --exchange nccl: steps covered by one all-gather")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1 result exchange: peer = the heads epilogue stores every rank's rows into all ranks' "
+                         "gather buffers over NVLink (no collective); nccl = all_gather_into_tensor per step")
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="device time to accumulate per mode by repeating the K-step region (median reported)")
     ap.add_argument("--max-regions", type=int, default=400)
@@ -324,16 +327,39 @@ def main():
     nstream = max(1, args.streams)
     streams = [torch.cuda.Stream(device=dev) for _ in range(nstream)]
     eng = model.engine()
+    peer = None
     if world > 1:
-        # N>1: the result blocks of all in-flight plans live in ONE ring, so that a group of consecutive
-        # steps is all-gathered by a single collective
-        ring = _OutRing(nstream)
-        eng.out_alloc = ring
+        n_out_blk = B * T[1] * (2 + 3 + 1 + 3 + eng.num_bins + eng.num_size)
+        if args.exchange == "peer" and eng.use_mega:
+            from frustum_convnet_b200.sharding import PeerResultExchange
+            try:
+                peer = PeerResultExchange(nstream, n_out_blk, dev)
+            except Exception as e:   # no P2P mapping on this box: keep the measured path honest, say so
+                sys.stderr.write("peer exchange unavailable (%r): falling back to NCCL all-gather\n" % (e,))
+                peer = None
+        if peer is not None:
+            slot_i = [0]
+
+            def peer_alloc(n, device):
+                v = peer.local_block(slot_i[0])
+                assert v.numel() == n
+                slot_i[0] += 1
+                return v
+            eng.out_alloc = peer_alloc
+        else:
+            # NCCL path: the result blocks of all in-flight plans live in ONE ring, so that a group of
+            # consecutive steps is all-gathered by a single collective
+            ring = _OutRing(nstream)
+            eng.out_alloc = ring
     plans = []
     for st in streams:
         with torch.cuda.stream(st):
             plans.append(eng.plan(B, one["point_cloud"].shape[2], T))
     eng.out_alloc = None
+    if peer is not None:
+        for k, pl in enumerate(plans):
+            blocks, flags = peer.peer_targets(k)
+            pl.set_peer_outputs(blocks, flags)
     plan = plans[0]
     # every pool entry is one packed block in the engine's input layout (one staging copy per step)
     host_pool, dev_pool = [], []
@@ -355,13 +381,13 @@ def main():
     G = max(1, min(nstream, args.gather_group))
     ngroup = (nstream + G - 1) // G
     gather_done = [None] * ngroup
-    if world > 1:
+    if world > 1 and peer is None:
         n_out = plans[0].out_flat.numel()
         assert all(pl.out_flat.data_ptr() == ring.buf.data_ptr() + 4 * n_out * k for k, pl in enumerate(plans))
         group_src = [ring.buf[g * G * n_out: min(nstream, (g + 1) * G) * n_out] for g in range(ngroup)]
         gather_bufs = [torch.empty((world, src.numel()), dtype=torch.float32, device=dev) for src in group_src]
     n_gathers = [0]
-    no_comm = os.environ.get("FCN_BENCH_NO_COMM") == "1"   # diagnostics: replicas without the result gather
+    no_comm = os.environ.get("FCN_BENCH_NO_COMM") == "1" or peer is not None   # peer path: no collective to issue
 
     def gather(g):
         for k in range(g * G, min(nstream, (g + 1) * G)):
@@ -556,6 +582,9 @@ def main():
             "cuda_graph": True, "precision": roofline["precision"], "streams_in_flight": nstream,
             "timing": "median of %d repeated %d-step regions (resident and e2e regions alternate)" % (spread["regions"], args.steps),
             "collective": ("none (single GPU)" if world == 1 else
+                           "none: the heads epilogue of every forward stores its %d KB result block into all %d ranks' "
+                           "gather buffers over NVLink peer memory (CUDA IPC) + one epoch flag per forward"
+                           % (plans[0].out_flat.numel() * 4 // 1024, world) if peer is not None else
                            "NCCL all_gather of the per-rank result blocks, one per %d steps (%d issued in this run)"
                            % (G, n_gathers[0]))},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(plan.in_flat.numel() * 4),

@@ -88,7 +88,7 @@ class MegaLayer(C.Structure):
         ("relu", C.c_int), ("round_out", C.c_int), ("up", C.c_int), ("Cout", C.c_int),
         ("P_m", C.c_int), ("T_out", C.c_int), ("n_rows", C.c_int),
         ("ld_out", C.c_int), ("P_store", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int),
-        ("is_heads", C.c_int), ("flag_base", C.c_int),
+        ("is_heads", C.c_int), ("flag_base", C.c_int), ("out_map", C.c_int), ("reserved0", C.c_int),
         ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
     ]
 
@@ -106,10 +106,12 @@ class MegaArgs(C.Structure):
     _fields_ = [
         ("n_layers", C.c_int), ("n_jobs", C.c_int), ("n_flags", C.c_int), ("grid", C.c_int),
         ("layers", C.c_void_p), ("jobs", C.c_void_p), ("tmaps", C.c_void_p), ("sync", C.c_void_p),
+        ("n_maps", C.c_int), ("reserved0", C.c_int),
         ("B", C.c_int), ("T", C.c_int), ("NH", C.c_int), ("NS", C.c_int),
         ("center_ref", C.c_void_p), ("mean_size", C.c_void_p),
         ("n_out", C.c_int), ("n_flag_out", C.c_int),
         ("outs", DecodeOut * MAX_PEERS), ("flag_out", C.c_void_p * MAX_PEERS),
+        ("dbg_clocks", C.c_void_p),
     ]
 
 
@@ -129,6 +131,7 @@ SIGNATURES = {
     "fcn_btc_to_bct": (_I, [_I, _I, _I, _I, _I, _P, _P, _P]),
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
     "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
+    "fcn_encode_store_map": (_I, [_P, _P, _I, _I]),
     "fcn_rbbox_iou_3d_pair": (_I, [_I, _P, _P, _P, _F, _P, _P]),
 }
 

@@ -263,3 +263,24 @@ extern "C" int fcn_encode_activation_map(void *out_map_128B, const float *base, 
     memcpy(out_map_128B, &m, 128);
     return FCN_OK;
 }
+
+extern "C" int fcn_encode_store_map(void *out_map_128B, const float *base, int rows, int inner) {
+    FCN_REQUIRE(out_map_128B && base, "NULL pointer");
+    FCN_REQUIRE(rows >= 1 && inner >= 32 && inner % 4 == 0, "bad shape");
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return fcn::invalid(__func__, "cuTensorMapEncodeTiled is not available in this driver");
+    CUtensorMap m;
+    const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, 1};
+    const cuuint64_t gstr[2] = {(cuuint64_t)inner * 4, (cuuint64_t)rows * inner * 4};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(fcn::g_err, sizeof(fcn::g_err), "%s: cuTensorMapEncodeTiled failed with CUresult %d", __func__, (int)r);
+        return FCN_ERR_CUDA;
+    }
+    memcpy(out_map_128B, &m, 128);
+    return FCN_OK;
+}

@@ -57,9 +57,9 @@ def job_order(layers: Sequence[LayerDesc]) -> List[int]:
 
 
 def build_tables(layers: Sequence[LayerDesc], interleave: bool = True):
-    """-> (map_keys, layer_rows, jobs).  map_keys: list of (source buffer name, stride) in map-index order;
-    layer_rows: dict per layer with map indices / flag bases; jobs: list of dicts
-    {layer, m, n, deps: [(first_flag, count, target)]} in execution order."""
+    """-> (map_keys, layer_rows, jobs, nflags).  map_keys: tensor maps in index order - ("load", buffer, stride) for
+    the A-operand boxes and ("store", buffer, up) for the epilogue stores; layer_rows: dict per layer with map
+    indices / flag bases; jobs: list of dicts {layer, m, n, deps: [(first_flag, count, target)]} in execution order."""
     producers: Dict[str, List[int]] = {}
     for i, L in enumerate(layers):
         producers.setdefault(L.out, []).append(i)
@@ -72,12 +72,16 @@ def build_tables(layers: Sequence[LayerDesc], interleave: bool = True):
     for i, L in enumerate(layers):
         segs = []
         for (src, c, tap, st) in L.segs:
-            key = (src, st)
+            key = ("load", src, st)
             if key not in map_idx:
                 map_idx[key] = len(map_keys)
                 map_keys.append(key)
             segs.append(dict(map_idx=map_idx[key], kblocks=(c + 31) // 32, tap=tap, stride=st))
-        rows.append(dict(segs=segs, flag_base=flag_base[i]))
+        okey = ("store", L.out, L.up)
+        if L.name != "heads" and okey not in map_idx:
+            map_idx[okey] = len(map_keys)
+            map_keys.append(okey)
+        rows.append(dict(segs=segs, flag_base=flag_base[i], out_map=map_idx.get(okey, 0)))
 
     def deps_of(li, m):
         L = layers[li]
@@ -151,7 +155,7 @@ def to_ctypes(layers: Sequence[LayerDesc], rows, jobs, ptrs):
         a.relu, a.round_out, a.up, a.Cout = L.relu, L.round_out, L.up, L.Cout
         a.P_m, a.T_out, a.n_rows = L.P_m, L.T_out, L.n_rows
         a.ld_out, a.P_store, a.T_store, a.c_off = L.ld_out, L.P_store, L.T_store, L.c_off
-        a.is_heads, a.flag_base = (1 if L.name == "heads" else 0), row["flag_base"]
+        a.is_heads, a.flag_base, a.out_map = (1 if L.name == "heads" else 0), row["flag_base"], row["out_map"]
         a.w_tc, a.bias, a.out = ptrs[i]
     JA = (_lib.MegaJob * max(len(jobs), 1))()
     for j, jb in enumerate(jobs):

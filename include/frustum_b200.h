@@ -185,7 +185,9 @@ FCN_API int fcn_decode_eval(int B, int T, int pitch, int ld, int num_heading_bin
  *                 packed TF32 weight image / bias, the output slice and the index of its completion counters;
  *        jobs   : one [128 rows x NT columns] output tile each, in TOPOLOGICAL order (a job depends only on jobs
  *                 with a smaller index), with the counters (first, count, target) it has to wait for;
- *        tmaps  : DEVICE array of 128-byte tensor maps (fcn_encode_activation_map), 64-byte aligned;
+ *        tmaps  : HOST array of n_maps (<= 48) 128-byte tensor maps - A-operand load maps
+ *                 (fcn_encode_activation_map) and epilogue store maps (fcn_encode_store_map); copied into the
+ *                 kernel parameters at launch, like the HOST layer table;
  *        sync   : DEVICE int32[4 + n_flags], zero-initialised ONCE by the caller; [0] job counter, [1] finished
  *                 CTAs, [2] epoch (forwards completed), [4..] per-(layer,row-tile) completion counters.  The
  *                 kernel resets [0],[1],[4..] itself at the end of every forward.
@@ -212,6 +214,7 @@ typedef struct {
     int P_m, T_out, n_rows;      /* GEMM row space: row r = b*P_m + t, valid iff t < T_out; n_rows = B*P_m */
     int ld_out, P_store, T_store, c_off;
     int is_heads, flag_base;
+    int out_map, reserved0;      /* tensor map of the epilogue's TMA store (fcn_encode_store_map); unused for heads */
     const void *w_tc;            /* packed stage images, N-tile major */
     const float *bias;
     float *out;
@@ -222,17 +225,25 @@ typedef struct {
 } fcn_mega_job;
 typedef struct {
     int n_layers, n_jobs, n_flags, grid;   /* grid: persistent CTAs (0 = one per SM) */
-    const fcn_mega_layer *layers;          /* device */
+    const fcn_mega_layer *layers;          /* HOST, n_layers (<= 24) records */
     const fcn_mega_job *jobs;              /* device */
-    const void *tmaps;                     /* device */
+    const void *tmaps;                     /* HOST, n_maps x 128 bytes */
     int32_t *sync;                         /* device */
+    int n_maps, reserved0;
     int B, T, NH, NS;                      /* decode: frustums, positions (T2), heading bins, size clusters */
     const float *center_ref, *mean_size;
     int n_out, n_flag_out;
     fcn_decode_out outs[FCN_MAX_PEERS];
     int32_t *flag_out[FCN_MAX_PEERS];
+    long long *dbg_clocks;                 /* optional (NULL): CTA 0 dumps 16 timestamps per job (first 64 jobs) */
 } fcn_mega_args;
 FCN_API int fcn_mega_forward(const fcn_mega_args *args, fcn_stream_t stream);
+
+/* TMA descriptor for the epilogue stores of the persistent FCN kernel: a position-major map viewed as
+ * (inner = up*ld floats, rows = flattened GEMM rows), box 32 x 32 with 128-byte swizzle.  For a transposed conv
+ * with `up` taps the GEMM row r, tap j lands on output row r*up + j: one tensor row = `up` consecutive output
+ * rows, the tap selects the inner offset j*ld.  Writes 128 bytes to HOST memory. */
+FCN_API int fcn_encode_store_map(void *out_map_128B, const float *base, int rows, int inner);
 
 /* Layout helpers for the channel-first module APIs: (B,C,T) <-> (B,pitch >= T,ld) position-major. */
 FCN_API int fcn_bct_to_btc(int B, int C, int T, int pitch, int ld, const float *src, float *dst,

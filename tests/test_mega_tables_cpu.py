@@ -110,7 +110,7 @@ def test_job_table_execution_reproduces_reference_fcn(golden_loader, name, seed)
 
 
 def test_full_size_car_table_shape():
-    """B=32 car: 648 jobs, 17 tensor maps, interleaved side deconvs; heads tiles wait for all three deconvs."""
+    """B=32 car: 648 jobs, 17 load + 13 store tensor maps, interleaved side deconvs; heads tiles wait for all three deconvs."""
     from frustum_convnet_b200 import config, synth
     cfg, w = config.load_workload("car")
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state_dict(w["arch"], 3, "KITTI", seed=7).items()}
@@ -119,7 +119,9 @@ def test_full_size_car_table_shape():
     plan = _Plan(eng, 32, 1024, (280, 140, 70, 35))
     descs = plan.mega_descs()
     map_keys, rows, jobs, nflags = mega.build_tables(descs)
-    assert len(jobs) == 648 and len(map_keys) == 17 and nflags == sum(d.m_tiles for d in descs)
+    loads = [k for k in map_keys if k[0] == "load"]
+    stores = [k for k in map_keys if k[0] == "store"]
+    assert len(jobs) == 648 and len(loads) == 17 and len(stores) == 13 and nflags == sum(d.m_tiles for d in descs)
     names = [descs[j["layer"]].name for j in jobs]
     first_d2, last_a3 = names.index("block2_deconv"), len(names) - 1 - names[::-1].index("block3_conv1")
     assert first_d2 < last_a3 and names.index("block3_conv1") < len(names) - 1 - names[::-1].index("block2_deconv")
