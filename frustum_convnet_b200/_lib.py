@@ -132,6 +132,9 @@ SIGNATURES = {
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
     "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
     "fcn_encode_store_map": (_I, [_P, _P, _I, _I]),
+    "fcn_ipc_export": (_I, [_P, _P, C.POINTER(C.c_longlong)]),
+    "fcn_ipc_open": (_I, [_P, C.POINTER(C.c_void_p)]),
+    "fcn_ipc_close": (_I, [_P]),
     "fcn_rbbox_iou_3d_pair": (_I, [_I, _P, _P, _P, _F, _P, _P]),
 }
 

@@ -482,22 +482,24 @@ class _Plan:
         (slot.cls_probs, slot.center, slot.heading, slot.size, slot.heading_probs, slot.size_probs) = \
             [_ptr(o) for o in outs]
 
-    def set_peer_outputs(self, peer_blocks, flag_ptrs=()):
-        """Multi-GPU result exchange without a collective: `peer_blocks` are flat fp32 blocks (this rank's slot
-        of every peer's gather buffer, mapped peer memory) with the layout of ``out_flat``; the heads epilogue
-        of the persistent FCN kernel stores the decoded rows into all of them over NVLink.  `flag_ptrs`: int32
-        device addresses that receive the forward's epoch number on completion."""
+    def set_peer_outputs(self, peer_block_ptrs, flag_ptrs=()):
+        """Multi-GPU result exchange without a collective: `peer_block_ptrs` are device ADDRESSES of flat fp32
+        blocks with the layout of ``out_flat`` (this rank's slot of every peer's gather buffer, peer memory mapped
+        with fcn_ipc_open); the heads epilogue of the persistent FCN kernel stores the decoded rows into all of
+        them over NVLink.  `flag_ptrs`: int32 device addresses that receive the forward's epoch number."""
         assert self.mega_args is not None, "peer outputs need the persistent FCN kernel (TF32 path)"
         assert self.graph is None, "set peer outputs before the first graph capture"
         m = self.mega_args
-        assert 1 + len(peer_blocks) <= _lib.MAX_PEERS and len(flag_ptrs) <= _lib.MAX_PEERS
-        self._peer_keepalive = list(peer_blocks)
-        for i, blk in enumerate(peer_blocks):
-            assert blk.dtype == torch.float32 and blk.numel() == self.out_flat.numel()
-            self._set_decode_out(m.outs[1 + i], self._views(blk))
-        m.n_out = 1 + len(peer_blocks)
+        assert 1 + len(peer_block_ptrs) <= _lib.MAX_PEERS and len(flag_ptrs) <= _lib.MAX_PEERS
+        base = self.out_flat.data_ptr()
+        offs = [o.data_ptr() - base for o in self.out]            # byte offsets of the six views in a block
+        for i, ptr in enumerate(peer_block_ptrs):
+            slot = m.outs[1 + i]
+            (slot.cls_probs, slot.center, slot.heading, slot.size, slot.heading_probs, slot.size_probs) = \
+                [int(ptr) + o for o in offs]
+        m.n_out = 1 + len(peer_block_ptrs)
         for i, fp in enumerate(flag_ptrs):
-            m.flag_out[i] = fp
+            m.flag_out[i] = int(fp)
         m.n_flag_out = len(flag_ptrs)
 
     def _launch_mega(self, center_ref2):

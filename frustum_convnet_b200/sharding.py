@@ -43,50 +43,66 @@ class PeerResultExchange:
     A per-(slot, rank) int32 epoch flag is raised in every peer when the forward is complete (system-scope
     release), which is what a downstream consumer polls.
 
-    Set-up (once): buffers are plain torch CUDA tensors; their CUDA-IPC handles travel through
-    ``torch.distributed.all_gather_object`` (torch.multiprocessing.reductions.reduce_tensor), peers are opened with
-    ``rebuild_cuda_tensor`` and peer access is enabled by a first device-to-device copy.  Raises if peer memory
-    cannot be mapped (the caller may then fall back to ``all_gather_into_tensor``)."""
+    Set-up (once): ONE torch CUDA tensor per rank holds blocks and flags; it is exported with ``fcn_ipc_export``
+    (CUDA-IPC handle of its allocation + offset), the handles travel through
+    ``torch.distributed.all_gather_object`` and every peer maps them with ``fcn_ipc_open`` on ITS OWN device
+    (lazy peer access).  Raises if peer memory cannot be mapped (the caller may then fall back to
+    ``all_gather_into_tensor``)."""
 
     def __init__(self, slots: int, block_numel: int, device: torch.device, group=None):
+        import ctypes as C
+
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
+
+        from . import _lib
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.slots, self.n = int(slots), int(block_numel)
         self.device = device
-        self.buf = torch.zeros((self.slots, self.world, self.n), dtype=torch.float32, device=device)
-        self.flags = torch.zeros((self.slots, self.world), dtype=torch.int32, device=device)
+        nblk = self.slots * self.world * self.n
+        nflag = self.slots * self.world
+        # a dedicated allocation > 1 MB: the caching allocator gives it its own cudaMalloc segment family; the
+        # export covers whatever allocation it lives in anyway (handle of the base + offset)
+        self.mem = torch.zeros(nblk + ((nflag + 3) // 4) * 4, dtype=torch.float32, device=device)
+        self.buf = self.mem[:nblk].view(self.slots, self.world, self.n)
+        self.flags = self.mem[nblk:nblk + nflag].view(torch.int32).view(self.slots, self.world)
         torch.cuda.synchronize(device)
-        mine = (reduce_tensor(self.buf), reduce_tensor(self.flags))
+        handle = (C.c_ubyte * 64)()
+        off = C.c_longlong(0)
+        with torch.cuda.device(device):
+            _lib.call("fcn_ipc_export", self.mem.data_ptr(), C.addressof(handle), C.byref(off))
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=group)
-        self.peer_buf, self.peer_flags = [], []
-        for r, ((fb, ab), (ff, af)) in enumerate(everyone):
+        dist.all_gather_object(everyone, (bytes(handle), int(off.value)), group=group)
+        self._opened = []
+        self.peer_base = []                                  # device address of every rank's `mem` as seen from here
+        for r, (h, o) in enumerate(everyone):
             if r == self.rank:
-                self.peer_buf.append(self.buf)
-                self.peer_flags.append(self.flags)
+                self.peer_base.append(self.mem.data_ptr())
                 continue
-            pb, pf = fb(*ab), ff(*af)                       # tensors living on the exporter's device
-            assert tuple(pb.shape) == tuple(self.buf.shape) and pb.dtype == torch.float32
-            # enable peer access from OUR device to the peer's (what a kernel here needs to store there)
-            if not torch.cuda.can_device_access_peer(device.index, pb.device.index):
-                raise RuntimeError("no peer access from cuda:%d to cuda:%d" % (device.index, pb.device.index))
-            probe = torch.zeros(1, dtype=torch.int32, device=device)
-            pf[0, self.rank:self.rank + 1].copy_(probe)     # device-to-device copy: torch enables P2P on first use
-            self.peer_buf.append(pb)
-            self.peer_flags.append(pf)
+            hb = (C.c_ubyte * 64).from_buffer_copy(h)
+            base = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.call("fcn_ipc_open", C.addressof(hb), C.byref(base))
+            self._opened.append(base.value)
+            self.peer_base.append(base.value + o)
+        self._flag_off = 4 * nblk
         torch.cuda.synchronize(device)
         dist.barrier(group=group)
+
+    def close(self):
+        from . import _lib
+        for b in self._opened:
+            _lib.call("fcn_ipc_close", b)
+        self._opened = []
 
     def local_block(self, slot: int) -> torch.Tensor:
         """Where THIS rank's results of `slot` live in its own gather buffer (use as the plan's output block)."""
         return self.buf[slot, self.rank]
 
     def peer_targets(self, slot: int):
-        """-> (list of peer blocks, list of flag addresses incl. the local one) for FrustumEngine plans."""
-        blocks = [self.peer_buf[r][slot, self.rank] for r in range(self.world) if r != self.rank]
-        flags = [self.peer_flags[r][slot, self.rank].data_ptr() for r in range(self.world)]
-        return blocks, flags
+        """-> (device addresses of this rank's block in every OTHER rank's buffer, flag addresses in ALL ranks)."""
+        blk = lambda r: self.peer_base[r] + 4 * ((slot * self.world + self.rank) * self.n)
+        flg = lambda r: self.peer_base[r] + self._flag_off + 4 * (slot * self.world + self.rank)
+        return ([blk(r) for r in range(self.world) if r != self.rank], [flg(r) for r in range(self.world)])
 
     def gathered(self, slot: int) -> torch.Tensor:
         """(world, block) view of everything gathered on this rank for `slot`."""

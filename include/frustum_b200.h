@@ -239,6 +239,16 @@ typedef struct {
 } fcn_mega_args;
 FCN_API int fcn_mega_forward(const fcn_mega_args *args, fcn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (5c) Multi-GPU plumbing for the result exchange by peer stores (one process per GPU): export a caller-owned
+ *      device buffer as a CUDA-IPC handle (+ the byte offset of `dev_ptr` inside its allocation), map an
+ *      exported buffer into this process for the current device, unmap it.  The mapped address (+ offset) is what
+ *      fcn_mega_args.outs[1..] / flag_out[] take.  handle = 64 bytes of HOST memory.
+ * ------------------------------------------------------------------------------------------ */
+FCN_API int fcn_ipc_export(const void *dev_ptr, void *handle_64B, long long *offset_bytes);
+FCN_API int fcn_ipc_open(const void *handle_64B, void **base_out);
+FCN_API int fcn_ipc_close(void *base);
+
 /* TMA descriptor for the epilogue stores of the persistent FCN kernel: a position-major map viewed as
  * (inner = up*ld floats, rows = flattened GEMM rows), box 32 x 32 with 128-byte swizzle.  For a transposed conv
  * with `up` taps the GEMM row r, tap j lands on output row r*up + j: one tensor row = `up` consecutive output
