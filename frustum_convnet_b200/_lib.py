@@ -115,6 +115,34 @@ class MegaArgs(C.Structure):
     ]
 
 
+class TrainSrc(C.Structure):
+    _fields_ = [("raw", C.c_void_p), ("grad", C.c_void_p), ("sums", C.c_void_p), ("gamma", C.c_void_p),
+                ("beta", C.c_void_p), ("count", C.c_double), ("Cstat", C.c_int), ("coff", C.c_int), ("relu", C.c_int),
+                ("ld", C.c_int), ("T", C.c_int), ("up", C.c_int), ("cup", C.c_int), ("c0", C.c_int)]
+
+
+class TrainSeg(C.Structure):
+    _fields_ = [("src", TrainSrc), ("C", C.c_int), ("tap", C.c_int), ("stride", C.c_int), ("s_ci", C.c_int),
+                ("w_off", C.c_longlong)]
+
+
+class TrainLayer(C.Structure):
+    _fields_ = [("B", C.c_int), ("T_out", C.c_int), ("n_seg", C.c_int), ("N", C.c_int), ("Cout", C.c_int),
+                ("up", C.c_int), ("s_co", C.c_int), ("s_j", C.c_int), ("has_bn", C.c_int), ("relu", C.c_int),
+                ("seg", TrainSeg * MAX_SEGS),
+                ("W", C.c_void_p), ("dW", C.c_void_p), ("bias", C.c_void_p), ("dbias", C.c_void_p),
+                ("Y", C.c_void_p), ("dA", C.c_void_p), ("sums", C.c_void_p), ("dsums", C.c_void_p),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("run_mean", C.c_void_p), ("run_var", C.c_void_p)]
+
+
+class TrainPool(C.Structure):
+    _fields_ = [("B", C.c_int), ("T", C.c_int), ("K", C.c_int), ("C", C.c_int), ("V", C.c_int), ("ld_feat", C.c_int),
+                ("Y", C.c_void_p), ("cnt", C.c_void_p), ("sums", C.c_void_p), ("gamma", C.c_void_p),
+                ("beta", C.c_void_p), ("one_hot", C.c_void_p), ("feat", C.c_void_p), ("argmax", C.c_void_p),
+                ("dfeat", C.c_void_p), ("dA", C.c_void_p)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
 _I, _F, _P = C.c_int, C.c_float, C.c_void_p
 SIGNATURES = {
@@ -132,6 +160,11 @@ SIGNATURES = {
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
     "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
     "fcn_encode_store_map": (_I, [_P, _P, _I, _I]),
+    "fcn_train_forward": (_I, [C.POINTER(TrainLayer), _P]),
+    "fcn_train_backward": (_I, [C.POINTER(TrainLayer), _I, _P]),
+    "fcn_train_pool": (_I, [C.POINTER(TrainPool), _I, _P]),
+    "fcn_train_finalize": (_I, [_P, _I, _I, _P]),
+    "fcn_adam_step": (_I, [_P, _P, _P, _P, C.c_longlong, _F, _F, _F, _F, _F, _I, _F, _P]),
     "fcn_ipc_export": (_I, [_P, _P, C.POINTER(C.c_longlong)]),
     "fcn_ipc_open": (_I, [_P, C.POINTER(C.c_void_p)]),
     "fcn_ipc_close": (_I, [_P]),

@@ -137,25 +137,33 @@ def _iou_metrics(c_metric, c_gt, thresh):
 
 
 def pointnet_det_torch(model, data):
-    cfg = get_cfg()
     pc = data.get("point_cloud")
     one_hot = data.get("one_hot")
-    cls_label, size_class = data.get("cls_label"), data.get("size_class")
-    center_label, heading_label, size_label = (data.get("box3d_center"), data.get("box3d_heading"),
-                                               data.get("box3d_size"))
     S = model.ARCH.num_scales
     centers = [data.get("center_ref%d" % (i + 1)) for i in range(S)]
-    B = pc.shape[0]
     xyz = pc[:, :3, :].contiguous()
     extra = pc[:, [3], :].contiguous() if pc.shape[1] > 3 else None
-    mean_size = torch.from_numpy(model.mean_size_array).type_as(pc)
     feats = model.feat_net(xyz, centers, extra, one_hot)
     x = model.conv_net(*feats)
     cls_scores, outputs = model.cls_out(x), model.reg_out(x)
-    num_out, osz = outputs.shape[2], outputs.shape[1]
+    osz = outputs.shape[1]
     cls_scores = cls_scores.permute(0, 2, 1).contiguous().view(-1, 2)
     outputs = outputs.permute(0, 2, 1).contiguous().view(-1, osz)
-    ref2 = centers[1].permute(0, 2, 1).contiguous().view(-1, 3)
+    return losses_from_logits(model, cls_scores, outputs, centers[1], data)
+
+
+def losses_from_logits(model, cls_scores, outputs, center_ref2, data):
+    """det_base.py:376-525 from the head logits on: ``cls_scores`` (B*T2, 2), ``outputs`` (B*T2, out) rows in
+    (frustum, position) order.  Eval decode without labels, else (losses, metrics)."""
+    cfg = get_cfg()
+    pc = data.get("point_cloud")
+    cls_label, size_class = data.get("cls_label"), data.get("size_class")
+    center_label, heading_label, size_label = (data.get("box3d_center"), data.get("box3d_heading"),
+                                               data.get("box3d_size"))
+    B = pc.shape[0]
+    num_out = cls_scores.shape[0] // B
+    mean_size = torch.from_numpy(model.mean_size_array).type_as(pc)
+    ref2 = center_ref2.permute(0, 2, 1).contiguous().view(-1, 3)
     cls_probs = F.softmax(cls_scores, -1)
     nb, ns = model.num_bins, model.num_size_cluster
 

@@ -255,6 +255,76 @@ FCN_API int fcn_ipc_close(void *base);
  * rows, the tap selects the inner offset j*ld.  Writes 128 bytes to HOST memory. */
 FCN_API int fcn_encode_store_map(void *out_map_128B, const float *base, int rows, int inner);
 
+/* ------------------------------------------------------------------------------------------
+ * (7) Training step (config 5, cfgs/refine_car.yaml): PointNetDet in train() mode on hand-written kernels.
+ *     Replaces the PyTorch/cuDNN autograd graph of models/det_base.py:62-224,367-368 (+ models/common.py:38-63
+ *     BatchNorm in batch-statistics mode) and the optimizer step (train/train_net_det.py:121-128,322-323).
+ *     All tensors are dense position-major fp32 [rows, channels]; rows = (frustum, position).  A layer is
+ *         Y = act(X) * W (+bias)          act = the PRODUCER's BatchNorm (batch statistics) + ReLU, applied while
+ *                                         the operand is loaded (no post-activation tensor exists)
+ *     and its backward applies the BatchNorm/ReLU backward on the fly as well (see csrc/train.cu).
+ *     Weights / gradients are addressed in the PARAMETER layout through strides:
+ *         W[segment channel c, column n] = W + w_off + c*s_ci + (n % Cout)*s_co + (n / Cout)*s_j
+ *     fcn_train_src: how a consumer sees a source tensor: position p of frustum b, channel c ->
+ *         raw[(b*T + p/up)*ld + c0 + (p%up)*cup + c]   (up > 1: un-shuffled output of a transposed conv)
+ *     `sums` (fp64 [2*Cstat]: Sum(y), Sum(y^2)) non-NULL = the source is a BN layer's raw output: apply
+ *     gamma*(y-mean)*invstd+beta (channel (coff + c) % Cstat, `count` samples per channel) and ReLU if `relu`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float *raw;
+    float *grad;                 /* gradient w.r.t. the POST-activation values, same layout as raw (may be NULL) */
+    const double *sums;
+    const float *gamma, *beta;
+    double count;
+    int Cstat, coff, relu;
+    int ld, T, up, cup, c0;
+} fcn_train_src;
+typedef struct {
+    fcn_train_src src;
+    int C, tap, stride, s_ci;
+    long long w_off;
+} fcn_train_seg;
+typedef struct {
+    int B, T_out, n_seg, N, Cout, up, s_co, s_j, has_bn, relu;
+    fcn_train_seg seg[FCN_MAX_SEGS];
+    const float *W;
+    float *dW;
+    const float *bias;           /* plain (no BN) layers only, else NULL */
+    float *dbias;
+    float *Y;                    /* raw output [B*T_out, N] */
+    float *dA;                   /* gradient w.r.t. this layer's post-activation output [B*T_out, N] */
+    double *sums;                /* [2*Cout] Sum(y), Sum(y^2): zeroed by the caller before the forward */
+    double *dsums;               /* [2*Cout] Sum(dz), Sum(dz*xh): zeroed by the caller before the backward */
+    const float *gamma, *beta;
+    float *dgamma, *dbeta, *run_mean, *run_var;
+} fcn_train_layer;
+FCN_API int fcn_train_forward(const fcn_train_layer *layer, fcn_stream_t stream);
+/* backward of one layer: column reduction, dW (all segments), dX for the segments in need_dx_mask */
+FCN_API int fcn_train_backward(const fcn_train_layer *layer, int need_dx_mask, fcn_stream_t stream);
+/* PointNet pooling: feat[(b,t), c] = (cnt > 0) * max_k relu(bn(Y[(b,t,k), c])), one-hot columns appended
+ * (det_base.py:100-101,134-157); backward scatters dfeat to the arg-max rows of a zero-filled dA. */
+typedef struct {
+    int B, T, K, C, V, ld_feat;
+    const float *Y;
+    const int32_t *cnt;
+    const double *sums;
+    const float *gamma, *beta, *one_hot;
+    float *feat;
+    int32_t *argmax;
+    const float *dfeat;
+    float *dA;
+} fcn_train_pool_args;
+FCN_API int fcn_train_pool(const fcn_train_pool_args *args, int backward, fcn_stream_t stream);
+/* end of step, one launch for all layers (DEVICE copy of the layer table): running statistics (momentum 0.1,
+ * unbiased variance), dgamma / dbeta / dbias from the reduction buffers */
+FCN_API int fcn_train_finalize(const fcn_train_layer *layers_dev, int n_layers, int update_running,
+                               fcn_stream_t stream);
+/* fused Adam over one flat bucket (torch.optim.Adam semantics incl. L2 weight decay); grad_scale multiplies
+ * the gradient first (1/world after a sum all-reduce) */
+FCN_API int fcn_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long long n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                          fcn_stream_t stream);
+
 /* Layout helpers for the channel-first module APIs: (B,C,T) <-> (B,pitch >= T,ld) position-major. */
 FCN_API int fcn_bct_to_btc(int B, int C, int T, int pitch, int ld, const float *src, float *dst,
                            fcn_stream_t stream);
