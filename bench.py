@@ -259,13 +259,183 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_train(args, rank, local_rank, world):
+    """Config 5 (BASELINE.json configs[4]): cfgs/refine_car.yaml TRAINING step on the hand-written kernels -
+    forward + losses + backward + gradient all-reduce (flat bucket, NCCL over NVLink, overlapped with the
+    PointNet backward) + fused Adam, B = --batch frustums per GPU (32 x 8 GPUs = 256)."""
+    import torch
+    import torch.distributed as dist
+    from frustum_convnet_b200 import config, synth
+    from frustum_convnet_b200.det_base import PointNetDet
+    from frustum_convnet_b200.train_engine import TrainStep
+    from frustum_convnet_b200 import train_path
+    assert torch.cuda.is_available(), "bench.py --train needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, w = config.load_workload("refine_car")
+    sd = synth.make_state_dict(w["arch"], 3, "KITTI", seed=7)
+
+    def build():
+        m = PointNetDet(3, num_vec=3)
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+        return m.to(dev).train()
+
+    model = build()
+    B = args.batch
+    ts = TrainStep(model, lr=cfg.TRAIN.BASE_LR, weight_decay=cfg.TRAIN.WEIGHT_DECAY)
+    npool = 64
+    host_pool = [{k: torch.from_numpy(v).pin_memory() for k, v in
+                  synth.make_frustums("refine_car", B, seed=1234 + rank + 1000 * i, with_labels=True).items()}
+                 for i in range(npool)]
+    dev_pool = [{k: v.to(dev) for k, v in d.items()} for d in host_pool]
+    h2d_bytes = int(sum(v.numel() * v.element_size() for v in host_pool[0].values()))
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host_pool[0].items()}
+
+    def step_resident(i):
+        return ts.step(dev_pool[i % npool])
+
+    def step_e2e(i):
+        for k, v in host_pool[i % npool].items():                 # H2D of this step's inputs + labels
+            stage[k].copy_(v, non_blocking=True)
+        losses, _ = ts.step(stage)
+        loss_host.copy_(losses["total_loss"].detach().reshape(1), non_blocking=True)   # D2H of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 10)):
+        step_resident(i)
+    for i in range(max(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    counters = {"res": 0, "e2e": 0}
+
+    def region(kind):
+        fn = step_resident if kind == "res" else step_e2e
+        base = counters[kind]
+        counters[kind] += args.steps
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            fn(base + i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    pilot = torch.tensor([region("res"), region("e2e")], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pilot, op=dist.ReduceOp.MAX)
+    R = int(min(max(np.ceil(args.min_seconds * 1e3 / max(float(pilot.min().item()), 1e-3)), 3), args.max_regions))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_regions = torch.zeros((2, R), dtype=torch.float64)
+    for r in range(R):
+        t_regions[0, r] = region("res")
+        t_regions[1, r] = region("e2e")
+    clocks = sampler.stop() if rank == 0 else None
+    t_regions = t_regions.to(dev)
+    if world > 1:
+        dist.all_reduce(t_regions, op=dist.ReduceOp.MAX)
+    t_regions = t_regions.cpu().numpy()
+    ms_step = float(np.median(t_regions[0])) / args.steps
+    e2e_ms = float(np.median(t_regions[1])) / args.steps
+    value, e2e_value = world * B / (ms_step * 1e-3), world * B / (e2e_ms * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- phase split of one step (CUDA events) and the PyTorch-autograd composition of the same branch (cuDNN, fp32)
+    eng = list(ts.engines.values())[0]
+    data = dev_pool[0]
+    S = 4
+    pc = data["point_cloud"][:, :3, :].contiguous()
+    centers = [data["center_ref%d" % (i + 1)].contiguous() for i in range(S)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    acc = np.zeros(4)
+    for it in range(20):
+        ev[0].record()
+        cls, reg = eng.forward(pc, centers, data["one_hot"])
+        ev[1].record()
+        cl, rl = cls.detach().clone().requires_grad_(True), reg.detach().clone().requires_grad_(True)
+        losses, _ = train_path.losses_from_logits(model, cl, rl, centers[1], data)
+        losses["total_loss"].backward()
+        ev[2].record()
+        ts.flat.grad.zero_()
+        eng.backward(cl.grad, rl.grad, update_running=False)
+        ev[3].record()
+        torch.cuda.synchronize()
+        acc += [ev[j].elapsed_time(ev[j + 1]) for j in range(3)] + [0.0]
+    phases = {"forward_ms": acc[0] / 20, "losses_torch_ms": acc[1] / 20, "backward_ms": acc[2] / 20}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref_model = build()
+    ref_model.train_kernels = False
+    opt = torch.optim.Adam(ref_model.parameters(), lr=cfg.TRAIN.BASE_LR, weight_decay=cfg.TRAIN.WEIGHT_DECAY)
+
+    def torch_step(d):
+        opt.zero_grad()
+        l, _ = ref_model(d)
+        l["total_loss"].backward()
+        opt.step()
+
+    for i in range(5):
+        torch_step(dev_pool[i])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(20):
+        torch_step(dev_pool[i % npool])
+    torch.cuda.synchronize()
+    autograd_ms = (time.perf_counter() - t0) / 20 * 1e3
+    gflop_step = 3.0 * 0.240 * B                       # SURVEY 8(d): refine car fwd 0.240 GFLOP/frustum, step ~ 3x
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12         # nominal fp32 FMA peak of the B200 (no measured figure)
+    line = {
+        "metric": "frustums/sec train step (fwd+bwd+allreduce+Adam)", "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "refine_car cfgs/refine_car.yaml TRAIN step, B=%d frustums/GPU x 512 pts, T=%s"
+                               % (B, list(eng.T)),
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "optimizer": "Adam lr %g wd %g (fused, flat bucket)" % (cfg.TRAIN.BASE_LR, cfg.TRAIN.WEIGHT_DECAY),
+                   "collective": "none (single GPU)" if world == 1 else
+                                 "NCCL all_reduce of the flat fp32 gradient bucket (%.2f MB) in 2 pieces, the first "
+                                 "overlapping the PointNet backward" % (ts.flat.numel * 4 / 1e6),
+                   "l2": "inputs cycle through a %d-batch pool; activations/gradients (~%d MB) exceed nothing: "
+                         "the step is launch/latency-bound" % (npool, 400),
+                   "timing": "median of %d repeated %d-step regions (resident and e2e regions alternate)" % (R, args.steps)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": eng.kernel_launches_per_step() * args.steps,
+        "launches_per_step": eng.kernel_launches_per_step(),
+        "phases_ms": phases,
+        "roofline": {"bound": "fp32", "kernel": "train step (all training kernels)", "achieved": gflop_step / ms_step,
+                     "peak": fp32_peak * 1e3, "unit": "GFLOP/s", "frac": gflop_step / ms_step / (fp32_peak * 1e3),
+                     "peak_source": "nominal fp32 FMA (148 SMs x 128 lanes x 2 x 1.965 GHz)", "traffic": None},
+        "cpu_baseline": None,
+        "autograd_gpu_baseline": {"value": B / (autograd_ms * 1e-3), "unit": UNIT, "ms_per_step": autograd_ms,
+                                  "kind": "same branch composed from PyTorch/cuDNN autograd ops on this GPU (fp32, "
+                                          "train_kernels=False) + torch.optim.Adam, wall clock"},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="car", choices=list(ALGO))
+    ap.add_argument("--workload", default="car", choices=list(ALGO) + ["refine_car"])
+    ap.add_argument("--train", action="store_true",
+                    help="config 5: time the refine_car TRAINING step (fwd+bwd+all-reduce+Adam) on the hand-written kernels")
     ap.add_argument("--batch", type=int, default=32, help="frustums per GPU per step")
     ap.add_argument("--precision", type=int, default=int(os.environ.get("FCN_PRECISION", "1")),
                     help="1: TF32 tensor cores (tcgen05) — the arithmetic cuDNN uses by default; 0: fp32 FMA")
@@ -288,6 +458,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     args.warmup = max(args.warmup, 3)
 
+    if args.train or args.workload == "refine_car":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "no CPU arm for the training step: the reference "
+                                  "train branch needs its CUDA grouping op (query_depth_point.py:23-24)"}))
+            return
+        run_train(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -399,6 +399,271 @@ __global__ void train_adam_kernel(float *__restrict__ p, const float *__restrict
     p[i] -= (lr / bc1) * (mi / denom);
 }
 
+
+// =====================================================================================================
+// Fast path for the PointNet layers 2/3 (97 % of the step's FLOPs): single source, 1x1 conv, rows map 1:1
+// (tap 0, stride 1, no pixel shuffle), channels and columns multiples of 16 / 64.  128 x 64 x 16 tiles,
+// 8 x 4 micro-tiles, float4 global loads along the contiguous axis, register prefetch of the next tile.
+// Same arithmetic (fp32 FMA, same on-the-fly BN / ReLU forward and backward) as the generic kernels above.
+// =====================================================================================================
+constexpr int FP_BM = 128, FP_BN = 64, FP_BK = 16, FP_THREADS = 256;
+
+#define FP_COMPUTE(As_, Bs_)                                                                        \
+    _Pragma("unroll") for (int kk = 0; kk < FP_BK; ++kk) {                                          \
+        const float4 a0 = *(const float4 *)&As_[kk][ty * 8], a1 = *(const float4 *)&As_[kk][ty * 8 + 4]; \
+        const float4 b0 = *(const float4 *)&Bs_[kk][tx * 4];                                        \
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};                       \
+        const float b[4] = {b0.x, b0.y, b0.z, b0.w};                                                \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i)                                               \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);  \
+    }
+
+__device__ __forceinline__ bool plain_layer(const fcn_train_layer &L) {
+    const fcn_train_seg &g = L.seg[0];
+    return L.n_seg == 1 && g.tap == 0 && g.stride == 1 && g.src.up == 1 && L.up == 1 && g.src.T == L.T_out &&
+           g.s_ci == 1 && g.C % FP_BK == 0 && L.N % FP_BN == 0 && g.src.c0 == 0 && g.src.ld % 4 == 0;
+}
+
+// Y[M,N] = act(X[M,K]) * W^T   (W in parameter layout (N,K): both operands contiguous along K)
+__global__ void __launch_bounds__(FP_THREADS)
+train_fwd_plain_kernel(const __grid_constant__ fcn_train_layer L) {
+    __shared__ __align__(16) float As[FP_BK][FP_BM + 4], Bs[FP_BK][FP_BN + 4];
+    __shared__ float s_scale[512], s_shift[512];
+    __shared__ float s_sum[FP_BN], s_sq[FP_BN];
+    const fcn_train_seg &g = L.seg[0];
+    const fcn_train_src &s = g.src;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int r0 = blockIdx.x * FP_BM, n0 = blockIdx.y * FP_BN;
+    const int M = L.B * L.T_out, K = g.C;
+    for (int c = tid; c < K; c += FP_THREADS) {
+        float sc = 1.f, sh = 0.f;
+        if (s.sums != nullptr) {
+            const BnCoef b = bn_coef(s.sums, s.gamma, s.beta, s.Cstat, (s.coff + c) % s.Cstat, 1.0 / s.count);
+            sc = b.scale; sh = b.shift;
+        }
+        s_scale[c] = sc; s_shift[c] = sh;
+    }
+    if (tid < FP_BN) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+    __syncthreads();
+    const bool act = s.sums != nullptr, relu = s.relu != 0;
+    // A: 128 rows x 16 k = 512 float4 (2 per thread); B: 64 n x 16 k = 256 float4 (1 per thread)
+    const int arow = tid / 4, akq = (tid % 4) * 4;
+    const int bn = tid / 4, bkq = (tid % 4) * 4;
+    float4 pa[2], pb;
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + arow + 64 * h;
+            pa[h] = r < M ? *(const float4 *)(s.raw + (size_t)r * s.ld + k0 + akq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        pb = *(const float4 *)(L.W + g.w_off + (size_t)(n0 + bn) * L.s_co + k0 + bkq);
+    };
+    auto sstore = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[4] = {pa[h].x, pa[h].y, pa[h].z, pa[h].w};
+            const bool ok = r0 + arow + 64 * h < M;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float x = v[i];
+                if (act) {
+                    x = fmaf(x, s_scale[k0 + akq + i], s_shift[k0 + akq + i]);
+                    if (relu) x = fmaxf(x, 0.f);
+                }
+                As[akq + i][arow + 64 * h] = ok ? x : 0.f;
+            }
+        }
+        Bs[bkq + 0][bn] = pb.x; Bs[bkq + 1][bn] = pb.y; Bs[bkq + 2][bn] = pb.z; Bs[bkq + 3][bn] = pb.w;
+    };
+    float acc[8][4] = {};
+    gload(0);
+    for (int k0 = 0; k0 < K; k0 += FP_BK) {
+        __syncthreads();
+        sstore(k0);
+        __syncthreads();
+        if (k0 + FP_BK < K) gload(k0 + FP_BK);
+        FP_COMPUTE(As, Bs)
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        float ps = 0.f, pq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + ty * 8 + i;
+            if (r < M) {
+                const float y = acc[i][j];
+                L.Y[(size_t)r * L.N + n] = y;
+                ps += y; pq += y * y;
+            }
+        }
+        atomicAdd(&s_sum[tx * 4 + j], ps);
+        atomicAdd(&s_sq[tx * 4 + j], pq);
+    }
+    __syncthreads();
+    if (tid < FP_BN) {
+        atomicAdd(&L.sums[n0 + tid], (double)s_sum[tid]);
+        atomicAdd(&L.sums[L.Cout + n0 + tid], (double)s_sq[tid]);
+    }
+}
+
+// dY(m, n) for 4 consecutive n (BN/ReLU backward on the fly), coefficient arrays in shared memory
+struct DyCoef {
+    float scale, shift, mean, invstd, m1, m2;
+};
+__device__ __forceinline__ float dy_apply(const DyCoef &c, float da, float y, bool relu) {
+    const float dz = (relu && fmaf(y, c.scale, c.shift) <= 0.f) ? 0.f : da;
+    return c.scale * (dz - c.m1 - (y - c.mean) * c.invstd * c.m2);
+}
+
+// dX[M,K] = dY[M,N] * W   (W (N,K): contiguous along K);  plain store (single consumer)
+__global__ void __launch_bounds__(FP_THREADS)
+train_dx_plain_kernel(const __grid_constant__ fcn_train_layer L) {
+    __shared__ __align__(16) float As[FP_BK][FP_BM + 4], Bs[FP_BK][FP_BN + 4];
+    __shared__ DyCoef s_c[512];
+    const fcn_train_seg &g = L.seg[0];
+    const fcn_train_src &s = g.src;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int r0 = blockIdx.x * FP_BM, c0 = blockIdx.y * FP_BN;
+    const int M = L.B * L.T_out, N = L.N;
+    for (int n = tid; n < N; n += FP_THREADS) {
+        const DyCtx c = dy_ctx(L, n);
+        s_c[n] = {c.scale, c.shift, c.mean, c.invstd, c.m1, c.m2};
+    }
+    __syncthreads();
+    const bool relu = L.relu != 0;
+    const int arow = tid / 4, anq = (tid % 4) * 4;          // dY tile: 128 rows x 16 n
+    const int bnr = tid / 16, bkq = (tid % 16) * 4;         // W tile: 16 n x 64 k
+    float4 pda[2], py[2], pb;
+    auto gload = [&](int n0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + arow + 64 * h;
+            if (r < M) {
+                pda[h] = *(const float4 *)(L.dA + (size_t)r * N + n0 + anq);
+                py[h] = *(const float4 *)(L.Y + (size_t)r * N + n0 + anq);
+            } else {
+                pda[h] = py[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        pb = *(const float4 *)(L.W + g.w_off + (size_t)(n0 + bnr) * L.s_co + c0 + bkq);
+    };
+    auto sstore = [&](int n0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float da[4] = {pda[h].x, pda[h].y, pda[h].z, pda[h].w}, y[4] = {py[h].x, py[h].y, py[h].z, py[h].w};
+            const bool ok = r0 + arow + 64 * h < M;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                As[anq + i][arow + 64 * h] = ok ? dy_apply(s_c[n0 + anq + i], da[i], y[i], relu) : 0.f;
+        }
+        *(float4 *)&Bs[bnr][bkq] = pb;
+    };
+    float acc[8][4] = {};
+    gload(0);
+    for (int n0 = 0; n0 < N; n0 += FP_BK) {
+        __syncthreads();
+        sstore(n0);
+        __syncthreads();
+        if (n0 + FP_BK < N) gload(n0 + FP_BK);
+        FP_COMPUTE(As, Bs)
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + ty * 8 + i;
+        if (r < M)
+            *(float4 *)(s.grad + (size_t)r * s.ld + c0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// dW[N,K] += dY[M,N]^T * act(X[M,K])   over the row slice [z*rows_per_block, ...): atomicAdd into the bucket
+__global__ void __launch_bounds__(FP_THREADS)
+train_dw_plain_kernel(const __grid_constant__ fcn_train_layer L, int rows_per_block) {
+    __shared__ __align__(16) float As[FP_BK][FP_BM + 4], Bs[FP_BK][FP_BN + 4];   // As[row][n], Bs[row][k]
+    __shared__ DyCoef s_c[FP_BM];
+    __shared__ float s_scale[FP_BN], s_shift[FP_BN];
+    const fcn_train_seg &g = L.seg[0];
+    const fcn_train_src &s = g.src;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int n0 = blockIdx.x * FP_BM, c0 = blockIdx.y * FP_BN;
+    const int M = L.B * L.T_out, N = L.N;
+    const int rb = blockIdx.z * rows_per_block, re = min(M, rb + rows_per_block);
+    if (tid < FP_BM) {
+        const int n = min(n0 + tid, N - 1);
+        const DyCtx c = dy_ctx(L, n);
+        s_c[tid] = {c.scale, c.shift, c.mean, c.invstd, c.m1, c.m2};
+    }
+    if (tid < FP_BN) {
+        float sc = 1.f, sh = 0.f;
+        if (s.sums != nullptr) {
+            const BnCoef b = bn_coef(s.sums, s.gamma, s.beta, s.Cstat, (s.coff + c0 + tid) % s.Cstat, 1.0 / s.count);
+            sc = b.scale; sh = b.shift;
+        }
+        s_scale[tid] = sc; s_shift[tid] = sh;
+    }
+    __syncthreads();
+    const bool relu = L.relu != 0, act = s.sums != nullptr, srelu = s.relu != 0;
+    // dY tile: 16 rows x 128 n = 512 float4 (2 per thread); X tile: 16 rows x 64 k = 256 float4 (1 per thread)
+    const int ar = tid / 32, anq = (tid % 32) * 4;
+    const int br = tid / 16, bkq = (tid % 16) * 4;
+    float4 pda[2], py[2], px;
+    const bool n_ok = n0 + anq < N;      // N % 64 == 0: a 128-wide tile may hang over by 64
+    auto gload = [&](int m0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = m0 + ar + 8 * h;
+            if (r < re && n_ok) {
+                pda[h] = *(const float4 *)(L.dA + (size_t)r * N + n0 + anq);
+                py[h] = *(const float4 *)(L.Y + (size_t)r * N + n0 + anq);
+            } else {
+                pda[h] = py[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const int r = m0 + br;
+        px = r < re ? *(const float4 *)(s.raw + (size_t)r * s.ld + c0 + bkq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto sstore = [&](int m0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool ok = m0 + ar + 8 * h < re && n_ok;
+            float4 o;
+            o.x = ok ? dy_apply(s_c[anq + 0], pda[h].x, py[h].x, relu) : 0.f;
+            o.y = ok ? dy_apply(s_c[anq + 1], pda[h].y, py[h].y, relu) : 0.f;
+            o.z = ok ? dy_apply(s_c[anq + 2], pda[h].z, py[h].z, relu) : 0.f;
+            o.w = ok ? dy_apply(s_c[anq + 3], pda[h].w, py[h].w, relu) : 0.f;
+            *(float4 *)&As[ar + 8 * h][anq] = o;
+        }
+        const bool ok = m0 + br < re;
+        float x[4] = {px.x, px.y, px.z, px.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (act) {
+                x[i] = fmaf(x[i], s_scale[bkq + i], s_shift[bkq + i]);
+                if (srelu) x[i] = fmaxf(x[i], 0.f);
+            }
+            if (!ok) x[i] = 0.f;
+        }
+        *(float4 *)&Bs[br][bkq] = make_float4(x[0], x[1], x[2], x[3]);
+    };
+    float acc[8][4] = {};
+    gload(rb);
+    for (int m0 = rb; m0 < re; m0 += FP_BK) {
+        __syncthreads();
+        sstore(m0);
+        __syncthreads();
+        if (m0 + FP_BK < re) gload(m0 + FP_BK);
+        FP_COMPUTE(As, Bs)
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = n0 + ty * 8 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            atomicAdd(&L.dW[g.w_off + (size_t)n * L.s_co + c0 + tx * 4 + j], acc[i][j]);
+    }
+}
+
 static int check_layer(const fcn_train_layer &L) {
     FCN_REQUIRE(L.B >= 1 && L.T_out >= 1 && L.N >= 1 && L.Cout >= 1 && L.up >= 1, "bad layer shape");
     FCN_REQUIRE(L.n_seg >= 1 && L.n_seg <= FCN_MAX_SEGS, "n_seg out of range");
@@ -412,6 +677,16 @@ static int check_layer(const fcn_train_layer &L) {
     return FCN_OK;
 }
 
+static bool host_plain(const fcn_train_layer &L, bool need_src_grad_layout) {
+    const fcn_train_seg &g = L.seg[0];
+    const bool ok = L.n_seg == 1 && g.tap == 0 && g.stride == 1 && g.src.up == 1 && L.up == 1 && g.src.T == L.T_out &&
+                    g.s_ci == 1 && g.C % 64 == 0 && g.C <= 512 && L.N % 64 == 0 && L.N <= 512 && g.src.c0 == 0 &&
+                    g.src.ld % 4 == 0 && g.w_off % 4 == 0 && L.s_co % 4 == 0 && L.has_bn && L.bias == nullptr &&
+                    L.Cout == L.N;
+    (void)need_src_grad_layout;
+    return ok;
+}
+
 }  // namespace fcn
 
 using namespace fcn;
@@ -420,8 +695,13 @@ extern "C" int fcn_train_forward(const fcn_train_layer *L, fcn_stream_t stream) 
     FCN_REQUIRE(L != nullptr, "NULL layer");
     if (int rc = check_layer(*L)) return rc;
     const int M = L->B * L->T_out;
-    dim3 grid(ceil_div(M, TG_BM), ceil_div(L->N, TG_BN));
-    train_fwd_kernel<<<grid, TG_THREADS, 0, (cudaStream_t)stream>>>(*L);
+    if (host_plain(*L, false)) {
+        dim3 grid(ceil_div(M, FP_BM), L->N / FP_BN);
+        train_fwd_plain_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(*L);
+    } else {
+        dim3 grid(ceil_div(M, TG_BM), ceil_div(L->N, TG_BN));
+        train_fwd_kernel<<<grid, TG_THREADS, 0, (cudaStream_t)stream>>>(*L);
+    }
     FCN_LAUNCH_CHECK();
     return FCN_OK;
 }
@@ -437,6 +717,18 @@ extern "C" int fcn_train_backward(const fcn_train_layer *L, int need_dx_mask, fc
         dim3 grid(ceil_div(L->N, 32), ceil_div(M, rpb));
         train_reduce_kernel<<<grid, 256, 0, st>>>(*L, rpb);
         FCN_LAUNCH_CHECK();
+    }
+    if (host_plain(*L, true)) {
+        const int rpb = 1024;
+        dim3 grid(ceil_div(L->N, FP_BM), L->seg[0].C / FP_BN, ceil_div(M, rpb));
+        train_dw_plain_kernel<<<grid, FP_THREADS, 0, st>>>(*L, rpb);
+        FCN_LAUNCH_CHECK();
+        if ((need_dx_mask & 1) && L->seg[0].src.grad != nullptr) {
+            dim3 gx(ceil_div(M, FP_BM), L->seg[0].C / FP_BN);
+            train_dx_plain_kernel<<<gx, FP_THREADS, 0, st>>>(*L);
+            FCN_LAUNCH_CHECK();
+        }
+        return FCN_OK;
     }
     for (int sg = 0; sg < L->n_seg; ++sg) {
         const int rpb = 512;

@@ -272,6 +272,7 @@ class PointNetDet(_EngineOwner):
         self.reg_out.bias.data.zero_()
         self.use_cuda_graph = default_cuda_graph()   # replay one CUDA graph per input shape (FCN_CUDA_GRAPH)
         self.copy_outputs = True      # False: return views of the engine's output block (zero-copy)
+        self.train_kernels = os.environ.get("FCN_TRAIN_KERNELS", "1") != "0"   # train(): csrc/train.cu, else autograd
 
     def _engine_spec(self):
         return self.ARCH, self.num_vec, self.dataset_name, self.feat_net.dists, self.num_bins, ""
@@ -284,7 +285,11 @@ class PointNetDet(_EngineOwner):
         has_labels = data_dicts.get("box3d_center") is not None
         if has_labels or self.training or point_cloud.shape[1] > 3:
             assert has_labels or not self.training, "Please provide labels for training."
-            from frustum_convnet_b200.train_path import pointnet_det_torch
+            from frustum_convnet_b200.train_path import pointnet_det_kernels, pointnet_det_torch
+            # train() mode with labels on a CUDA xyz cloud: hand-written training kernels (csrc/train.cu);
+            # everything else (label inputs in eval mode, extra point features, train_kernels = False): torch ops
+            if self.training and has_labels and self.train_kernels and point_cloud.is_cuda and point_cloud.shape[1] == 3:
+                return pointnet_det_kernels(self, data_dicts)
             return pointnet_det_torch(self, data_dicts)
         xyz = point_cloud[:, :3, :].contiguous()
         out = self.engine().forward(xyz, [c.contiguous() for c in centers],

@@ -48,7 +48,6 @@ class FlatParams:
             k = p.numel()
             self.param[off: off + k].copy_(p.data.reshape(-1))
             p.data = self.param[off: off + k].view(p.shape)
-            p.grad = self.grad[off: off + k].view(p.shape)
             self.offsets[id(p)] = off
             off += k
         self.numel = n
@@ -56,15 +55,35 @@ class FlatParams:
     def gptr(self, p) -> int:
         return self.grad.data_ptr() + 4 * self.offsets[id(p)]
 
+    def grad_view(self, p) -> torch.Tensor:
+        off = self.offsets[id(p)]
+        return self.grad[off: off + p.numel()].view(p.shape)
 
-class _Buf:
-    """One activation: raw output Y, gradient dA w.r.t. its post-activation value, BN reduction buffers."""
+    def expose_grads(self, module):
+        """``p.grad`` = view of the flat bucket (what an optimizer or a test reads after TrainStep.forward_backward)."""
+        for p in module.parameters():
+            p.grad = self.grad_view(p)
 
-    def __init__(self, rows, cols, dev, bn_channels=0, need_grad=True):
-        self.Y = torch.empty((rows, cols), dtype=torch.float32, device=dev)
-        self.rows, self.cols, self.bn = rows, cols, bn_channels
-        self.dA = None
-        self.need_grad = need_grad
+
+class LogitsFn(torch.autograd.Function):
+    """autograd bridge for the reference's own training loop (``losses, _ = model(data); loss.backward();
+    optimizer.step()``, train/train_net_det.py:121-128): forward = the kernel forward up to the head logits,
+    backward = the kernel backward; parameter gradients are returned to autograd as copies of the flat bucket."""
+
+    @staticmethod
+    def forward(ctx, eng, pc, one_hot, ncent, *rest):
+        centers, params = rest[:ncent], rest[ncent:]
+        cls, reg = eng.forward(pc, list(centers), one_hot)
+        ctx.eng, ctx.params, ctx.ncent = eng, params, ncent
+        return cls.clone(), reg.clone()
+
+    @staticmethod
+    def backward(ctx, dcls, dreg):
+        eng = ctx.eng
+        eng.flat.grad.zero_()
+        eng.backward(dcls.contiguous(), dreg.contiguous())
+        grads = tuple(eng.flat.grad_view(p).clone() for p in ctx.params)
+        return (None, None, None, None) + (None,) * ctx.ncent + grads
 
 
 class TrainEngine:
@@ -290,25 +309,33 @@ class TrainEngine:
         return self.act["cls_out"]["Y"], self.act["reg_out"]["Y"]
 
     @torch.no_grad()
-    def backward(self, dcls, dreg, update_running=True):
-        """dlogits -> gradients of every parameter, ACCUMULATED into the flat bucket ``self.flat.grad``."""
+    def backward(self, dcls, dreg, update_running=True, stage="all"):
+        """dlogits -> gradients of every parameter, ACCUMULATED into the flat bucket ``self.flat.grad``.
+        stage = "fcn" (heads + ConvFeatNet: everything the feat_net gradients depend on), "pointnet" (the rest +
+        BN bookkeeping) or "all"."""
         st = _stream()
-        torch._foreach_zero_(self._zero_bwd)
-        self.act["cls_out"]["dA"].copy_(dcls.reshape(self.act["cls_out"]["dA"].shape))
-        self.act["reg_out"]["dA"].copy_(dreg.reshape(self.act["reg_out"]["dA"].shape))
         S = len(self.T)
-        # FCN + heads in reverse creation order (a topological order of the backward graph: every consumer of a
-        # tensor was created after it)
-        for li in range(len(self.layers) - 1, self.n_pn_layers - 1, -1):
-            _lib.call("fcn_train_backward", C.byref(self.layers[li]), self.dx_mask[li], st)
-        for s in range(S - 1, -1, -1):
-            _lib.call("fcn_train_pool", C.byref(self.pools[s]), 1, st)
-            for j in (2, 1, 0):
-                li = 3 * s + j
+        if stage in ("all", "fcn"):
+            torch._foreach_zero_(self._zero_bwd)
+            self.act["cls_out"]["dA"].copy_(dcls.reshape(self.act["cls_out"]["dA"].shape))
+            self.act["reg_out"]["dA"].copy_(dreg.reshape(self.act["reg_out"]["dA"].shape))
+            # FCN + heads in reverse creation order (a topological order of the backward graph: every consumer of
+            # a tensor was created after it)
+            for li in range(len(self.layers) - 1, self.n_pn_layers - 1, -1):
                 _lib.call("fcn_train_backward", C.byref(self.layers[li]), self.dx_mask[li], st)
-        _lib.call("fcn_train_finalize", _ptr(self.table_dev), len(self.layers), 1 if update_running else 0, st)
-        if update_running and self._bn_counters:
-            torch._foreach_add_(self._bn_counters, 1)
+            # BN bookkeeping of the FCN layers: their dgamma / dbeta belong to the first gradient bucket
+            nf = len(self.layers) - self.n_pn_layers
+            _lib.call("fcn_train_finalize", _ptr(self.table_dev) + self.n_pn_layers * C.sizeof(_lib.TrainLayer), nf,
+                      1 if update_running else 0, st)
+        if stage in ("all", "pointnet"):
+            for s in range(S - 1, -1, -1):
+                _lib.call("fcn_train_pool", C.byref(self.pools[s]), 1, st)
+                for j in (2, 1, 0):
+                    li = 3 * s + j
+                    _lib.call("fcn_train_backward", C.byref(self.layers[li]), self.dx_mask[li], st)
+            _lib.call("fcn_train_finalize", _ptr(self.table_dev), self.n_pn_layers, 1 if update_running else 0, st)
+            if update_running and self._bn_counters:
+                torch._foreach_add_(self._bn_counters, 1)
 
     def kernel_launches_per_step(self):
         n_fwd = len(self.layers) + len(self.pools) + 2
@@ -328,6 +355,10 @@ class TrainStep:
         self.step_count = 0
         self.flat = None
         self.m = self.v = None
+        self._comm = None
+        self._split = 0
+        self._loss_graphs = {}
+        self.use_loss_graph = True     # losses + their backward as one CUDA graph (train_path.LossGraph)
 
     def engine(self, B, N, T) -> TrainEngine:
         key = (int(B), int(N), tuple(int(t) for t in T))
@@ -340,6 +371,21 @@ class TrainStep:
                 self.v = torch.zeros_like(self.flat.param)
         return e
 
+    def _losses(self, eng, cls, reg, center_ref2, data):
+        """-> (losses, metrics, dcls, dreg)."""
+        from .train_path import LossGraph, losses_from_logits
+        if self.use_loss_graph:
+            key = (eng.B, eng.T2)
+            lg = self._loss_graphs.get(key)
+            if lg is None:
+                lg = self._loss_graphs[key] = LossGraph(self.model, eng.B, eng.T2, reg.shape[1], cls.device)
+            return lg.run(cls, reg, center_ref2, data)
+        cls_l = cls.detach().clone().requires_grad_(True)
+        reg_l = reg.detach().clone().requires_grad_(True)
+        losses, metrics = losses_from_logits(self.model, cls_l, reg_l, center_ref2, data)
+        losses["total_loss"].backward()
+        return losses, metrics, cls_l.grad, reg_l.grad
+
     def forward_backward(self, data, update_running=True):
         """-> (losses, metrics); gradients (this rank's) are left in the flat bucket."""
         from .train_path import losses_from_logits
@@ -350,19 +396,47 @@ class TrainStep:
         eng = self.engine(pc.shape[0], pc.shape[2], [c.shape[2] for c in centers])
         self.flat.grad.zero_()
         cls, reg = eng.forward(pc, centers, data.get("one_hot"))
-        cls_l = cls.detach().clone().requires_grad_(True)
-        reg_l = reg.detach().clone().requires_grad_(True)
-        losses, metrics = losses_from_logits(model, cls_l, reg_l, centers[1], data)
-        losses["total_loss"].backward()
-        eng.backward(cls_l.grad, reg_l.grad, update_running=update_running)
+        losses, metrics, dcls, dreg = self._losses(eng, cls, reg, centers[1], data)
+        eng.backward(dcls, dreg, update_running=update_running)
+        self.flat.expose_grads(model)
         return losses, metrics
 
     def step(self, data):
+        """forward + losses + backward + gradient all-reduce + Adam.  With world > 1 the flat bucket is reduced in
+        TWO pieces on a communication stream: the FCN + heads part (92 % of the parameters, complete after the
+        first ~15 % of the backward) overlaps the PointNet backward; the PointNet part follows."""
         import torch.distributed as dist
-        losses, metrics = self.forward_backward(data)
+        from .train_path import losses_from_logits
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        model = self.model
+        S = model.ARCH.num_scales
+        pc = data["point_cloud"][:, :3, :].contiguous()
+        centers = [data["center_ref%d" % (i + 1)].contiguous() for i in range(S)]
+        eng = self.engine(pc.shape[0], pc.shape[2], [c.shape[2] for c in centers])
+        self.flat.grad.zero_()
+        cls, reg = eng.forward(pc, centers, data.get("one_hot"))
+        losses, metrics, dcls, dreg = self._losses(eng, cls, reg, centers[1], data)
         if world > 1:
-            dist.all_reduce(self.flat.grad)                      # one flat bucket: 13.27 MB (KITTI model)
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(device=self.flat.grad.device)
+                first = next(model.conv_net.parameters())
+                self._split = self.flat.offsets[id(first)]        # [0, split): feat_net, [split, n): conv_net + heads
+            cur = torch.cuda.current_stream()
+            eng.backward(dcls, dreg, stage="fcn")
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._comm.wait_event(ev)
+            with torch.cuda.stream(self._comm):
+                dist.all_reduce(self.flat.grad[self._split:])
+            eng.backward(None, None, stage="pointnet")
+            ev2 = torch.cuda.Event()
+            ev2.record(cur)
+            self._comm.wait_event(ev2)
+            with torch.cuda.stream(self._comm):
+                dist.all_reduce(self.flat.grad[: self._split])
+            cur.wait_stream(self._comm)
+        else:
+            eng.backward(dcls, dreg)
         self.step_count += 1
         self.model.refresh()       # parameters change behind autograd's version counters: eval pack must rebuild
         _lib.call("fcn_adam_step", _ptr(self.flat.param), _ptr(self.flat.grad), _ptr(self.m), _ptr(self.v),
