@@ -160,7 +160,8 @@ SIGNATURES = {
     "fcn_selftest_umma": (_I, [_I, _I, _P, _P, _P, _P]),
     "fcn_encode_activation_map": (_I, [_P, _P, _I, _I, _I, _I]),
     "fcn_encode_store_map": (_I, [_P, _P, _I, _I]),
-    "fcn_train_forward": (_I, [C.POINTER(TrainLayer), _P]),
+    "fcn_train_forward": (_I, [C.POINTER(TrainLayer), _P, C.c_longlong, _P]),
+    "fcn_train_workspace_floats": (C.c_longlong, [C.POINTER(TrainLayer)]),
     "fcn_train_backward": (_I, [C.POINTER(TrainLayer), _I, _P]),
     "fcn_train_pool": (_I, [C.POINTER(TrainPool), _I, _P]),
     "fcn_train_finalize": (_I, [_P, _I, _I, _P]),

@@ -88,20 +88,31 @@ __device__ __forceinline__ size_t w_index(const fcn_train_layer &L, const fcn_tr
 }
 
 // ------------------------------------------------------------------ forward GEMM + statistics
+// The FCN layers of the refinement stage are SKINNY (M = B*T = 96..640 rows, K up to 1536): a (M/64, N/64) grid
+// is 4-32 CTAs, each with a long serial K loop (measured 100-270 us per layer).  The K tiles of all segments
+// are therefore linearised and split over gridDim.z; slices write partial sums to a workspace and
+// train_fwd_finish_kernel adds them in a fixed order (deterministic), adds the bias, stores Y and accumulates
+// the batch statistics.  gridDim.z == 1 stores Y / statistics directly.
 __global__ void __launch_bounds__(TG_THREADS)
-train_fwd_kernel(const __grid_constant__ fcn_train_layer L) {
+train_fwd_kernel(const __grid_constant__ fcn_train_layer L, float *__restrict__ partial, int tiles_per_slice) {
     __shared__ float As[TG_BK][TG_BM + 4], Bs[TG_BK][TG_BN + 4];
     __shared__ float s_scale[TG_BK], s_shift[TG_BK];
     __shared__ float s_sum[TG_BN], s_sq[TG_BN];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int r0 = blockIdx.x * TG_BM, n0 = blockIdx.y * TG_BN;
     const int M = L.B * L.T_out;
+    const int q_lo = blockIdx.z * tiles_per_slice, q_hi = q_lo + tiles_per_slice;
     float acc[4][4] = {};
+    int q0 = 0;                                              // first linear K tile of the current segment
     for (int sg = 0; sg < L.n_seg; ++sg) {
         const fcn_train_seg &g = L.seg[sg];
         const fcn_train_src &s = g.src;
         const double inv = s.sums != nullptr ? 1.0 / s.count : 0.0;
-        for (int k0 = 0; k0 < g.C; k0 += TG_BK) {
+        const int nt = (g.C + TG_BK - 1) / TG_BK;
+        const int t_lo = max(q_lo - q0, 0), t_hi = min(q_hi - q0, nt);
+        q0 += nt;
+        for (int t = t_lo; t < t_hi; ++t) {
+            const int k0 = t * TG_BK;
             __syncthreads();
             if (tid < TG_BK) {
                 const int c = k0 + tid;
@@ -119,8 +130,8 @@ train_fwd_kernel(const __grid_constant__ fcn_train_layer L) {
                 const int rr = ty + 16 * i, r = r0 + rr, c = k0 + tx;
                 float v = 0.f;
                 if (r < M && c < g.C) {
-                    const int b = r / L.T_out, t = r - b * L.T_out;
-                    v = src_act(s, b, t * g.stride + g.tap, c, s_scale[tx], s_shift[tx]);
+                    const int b = r / L.T_out, tt = r - b * L.T_out;
+                    v = src_act(s, b, tt * g.stride + g.tap, c, s_scale[tx], s_shift[tx]);
                 }
                 As[tx][rr] = v;
             }
@@ -144,6 +155,20 @@ train_fwd_kernel(const __grid_constant__ fcn_train_layer L) {
                     for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
             }
         }
+    }
+    if (gridDim.z > 1) {                                     // partial sums of this K slice
+        float *dst = partial + (size_t)blockIdx.z * M * L.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = r0 + ty * 4 + i;
+            if (r >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx * 4 + j;
+                if (n < L.N) dst[(size_t)r * L.N + n] = acc[i][j];
+            }
+        }
+        return;
     }
     // epilogue: store raw output (+bias), per-channel Sum(y), Sum(y^2)
     if (tid < TG_BN) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
@@ -173,6 +198,38 @@ train_fwd_kernel(const __grid_constant__ fcn_train_layer L) {
             atomicAdd(&L.sums[co], (double)s_sum[tid]);
             atomicAdd(&L.sums[L.Cout + co], (double)s_sq[tid]);
         }
+    }
+}
+
+// Y = sum over K slices (fixed order) + bias; batch statistics.  Block = 32 columns x 8 row lanes.
+__global__ void __launch_bounds__(256)
+train_fwd_finish_kernel(const __grid_constant__ fcn_train_layer L, const float *__restrict__ partial, int nslice,
+                        int rows_per_block) {
+    const int nl = threadIdx.x % 32, rl = threadIdx.x / 32;
+    const int n = blockIdx.x * 32 + nl;
+    const int M = L.B * L.T_out;
+    const int rb = blockIdx.y * rows_per_block, re = min(M, rb + rows_per_block);
+    __shared__ float s1[8][33], s2[8][33];
+    float a1 = 0.f, a2 = 0.f;
+    if (n < L.N) {
+        const float bias = L.bias != nullptr ? L.bias[n] : 0.f;
+        for (int r = rb + rl; r < re; r += 8) {
+            float y = bias;
+            for (int z = 0; z < nslice; ++z) y += partial[((size_t)z * M + r) * L.N + n];
+            L.Y[(size_t)r * L.N + n] = y;
+            a1 += y; a2 += y * y;
+        }
+    }
+    if (!L.has_bn) return;
+    s1[rl][nl] = a1; s2[rl][nl] = a2;
+    __syncthreads();
+    if (rl == 0 && n < L.N) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { t1 += s1[i][nl]; t2 += s2[i][nl]; }
+        const int co = n % L.Cout;
+        atomicAdd(&L.sums[co], (double)t1);
+        atomicAdd(&L.sums[L.Cout + co], (double)t2);
     }
 }
 
@@ -281,7 +338,7 @@ train_dw_kernel(const __grid_constant__ fcn_train_layer L, int seg_idx, int rows
 
 // ------------------------------------------------------------------ backward: dX(seg) += dY * W^T
 __global__ void __launch_bounds__(TG_THREADS)
-train_dx_kernel(const __grid_constant__ fcn_train_layer L, int seg_idx) {
+train_dx_kernel(const __grid_constant__ fcn_train_layer L, int seg_idx, int n_per_slice) {
     __shared__ float As[TG_BK][TG_BM + 4], Bs[TG_BK][TG_BN + 4];   // As[n][row], Bs[n][channel]
     __shared__ DyCtx s_dy[TG_BK];
     const fcn_train_seg &g = L.seg[seg_idx];
@@ -290,19 +347,20 @@ train_dx_kernel(const __grid_constant__ fcn_train_layer L, int seg_idx) {
     const int r0 = blockIdx.x * TG_BM, c0 = blockIdx.y * TG_BN;
     const int M = L.B * L.T_out;
     float acc[4][4] = {};
-    for (int nn0 = 0; nn0 < L.N; nn0 += TG_BK) {
+    const int n_lo = blockIdx.z * n_per_slice, n_hi = min(L.N, n_lo + n_per_slice);
+    for (int nn0 = n_lo; nn0 < n_hi; nn0 += TG_BK) {
         __syncthreads();
         if (tid < TG_BK) s_dy[tid] = dy_ctx(L, min(nn0 + tid, L.N - 1));
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {       // dY tile: 64 rows x 16 columns (consecutive threads -> consecutive n)
             const int rr = ty + 16 * i, r = r0 + rr, n = nn0 + tx;
-            As[tx][rr] = (r < M && n < L.N) ? dy_elem(L, s_dy[tx], r, n) : 0.f;
+            As[tx][rr] = (r < M && n < n_hi) ? dy_elem(L, s_dy[tx], r, n) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {       // W tile: 16 columns x 64 channels
             const int kk = tid / 64 + 4 * i, cc = tid % 64, n = nn0 + kk, c = c0 + cc;
-            Bs[kk][cc] = (n < L.N && c < g.C) ? L.W[w_index(L, g, c, n)] : 0.f;
+            Bs[kk][cc] = (n < n_hi && c < g.C) ? L.W[w_index(L, g, c, n)] : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -691,18 +749,52 @@ static bool host_plain(const fcn_train_layer &L, bool need_src_grad_layout) {
 
 using namespace fcn;
 
-extern "C" int fcn_train_forward(const fcn_train_layer *L, fcn_stream_t stream) {
+// K slices of the generic forward GEMM for this layer (1 = no split); `workspace_floats` bounds the partial sums
+static int fwd_slices(const fcn_train_layer &L, long long workspace_floats, int *tiles_per_slice) {
+    const int M = L.B * L.T_out;
+    int tiles = 0;
+    for (int i = 0; i < L.n_seg; ++i) tiles += ceil_div(L.seg[i].C, TG_BK);
+    const int ctas = ceil_div(M, TG_BM) * ceil_div(L.N, TG_BN);
+    int want = ceil_div(2 * 148, ctas);                      // ~2 CTAs per SM in total
+    if (want > tiles / 2) want = tiles / 2;                  // at least two K tiles per slice
+    const long long fit = workspace_floats / ((long long)M * L.N);
+    if (want > fit) want = (int)fit;
+    if (want < 2) { *tiles_per_slice = tiles; return 1; }
+    *tiles_per_slice = ceil_div(tiles, want);
+    return ceil_div(tiles, *tiles_per_slice);
+}
+
+extern "C" long long fcn_train_workspace_floats(const fcn_train_layer *L) {
+    // enough for the split the launcher would like to use: 2*148 CTAs' worth of partial tiles, at most K/32 slices
+    if (L == nullptr) return 0;
+    int tps = 0;
+    const int n = fwd_slices(*L, (long long)1 << 40, &tps);
+    return n > 1 ? (long long)n * L->B * L->T_out * L->N : 0;
+}
+
+extern "C" int fcn_train_forward(const fcn_train_layer *L, float *workspace, long long workspace_floats,
+                                 fcn_stream_t stream) {
     FCN_REQUIRE(L != nullptr, "NULL layer");
     if (int rc = check_layer(*L)) return rc;
     const int M = L->B * L->T_out;
+    cudaStream_t st = (cudaStream_t)stream;
     if (host_plain(*L, false)) {
         dim3 grid(ceil_div(M, FP_BM), L->N / FP_BN);
-        train_fwd_plain_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(*L);
-    } else {
-        dim3 grid(ceil_div(M, TG_BM), ceil_div(L->N, TG_BN));
-        train_fwd_kernel<<<grid, TG_THREADS, 0, (cudaStream_t)stream>>>(*L);
+        train_fwd_plain_kernel<<<grid, FP_THREADS, 0, st>>>(*L);
+        FCN_LAUNCH_CHECK();
+        return FCN_OK;
     }
+    int tps = 0;
+    const int nslice = workspace != nullptr ? fwd_slices(*L, workspace_floats, &tps) : (fwd_slices(*L, 0, &tps), 1);
+    dim3 grid(ceil_div(M, TG_BM), ceil_div(L->N, TG_BN), nslice);
+    train_fwd_kernel<<<grid, TG_THREADS, 0, st>>>(*L, workspace, tps);
     FCN_LAUNCH_CHECK();
+    if (nslice > 1) {
+        const int rpb = 32;
+        dim3 gf(ceil_div(L->N, 32), ceil_div(M, rpb));
+        train_fwd_finish_kernel<<<gf, 256, 0, st>>>(*L, workspace, nslice, rpb);
+        FCN_LAUNCH_CHECK();
+    }
     return FCN_OK;
 }
 
@@ -713,7 +805,7 @@ extern "C" int fcn_train_backward(const fcn_train_layer *L, int need_dx_mask, fc
     const int M = L->B * L->T_out;
     cudaStream_t st = (cudaStream_t)stream;
     {   // Sum(dz), Sum(dz * xh) per channel
-        const int rpb = 256;
+        const int rpb = M >= 4096 ? 256 : 32;
         dim3 grid(ceil_div(L->N, 32), ceil_div(M, rpb));
         train_reduce_kernel<<<grid, 256, 0, st>>>(*L, rpb);
         FCN_LAUNCH_CHECK();
@@ -731,13 +823,22 @@ extern "C" int fcn_train_backward(const fcn_train_layer *L, int need_dx_mask, fc
         return FCN_OK;
     }
     for (int sg = 0; sg < L->n_seg; ++sg) {
-        const int rpb = 512;
+        // split the reduction (rows for dW, columns for dX) until ~2 CTAs per SM exist: the layers are skinny and
+        // a handful of CTAs with long serial loops was the measured bottleneck (outputs are atomic accumulations)
+        const int cw = ceil_div(L->seg[sg].C, TG_BM) * ceil_div(L->N, TG_BN);
+        int zs = ceil_div(2 * 148, cw);
+        int rpb = ceil_div(ceil_div(M, zs), TG_BK) * TG_BK;
+        if (rpb < 2 * TG_BK) rpb = 2 * TG_BK;
         dim3 grid(ceil_div(L->seg[sg].C, TG_BM), ceil_div(L->N, TG_BN), ceil_div(M, rpb));
         train_dw_kernel<<<grid, TG_THREADS, 0, st>>>(*L, sg, rpb);
         FCN_LAUNCH_CHECK();
         if (((need_dx_mask >> sg) & 1) && L->seg[sg].src.grad != nullptr) {
-            dim3 gx(ceil_div(M, TG_BM), ceil_div(L->seg[sg].C, TG_BN));
-            train_dx_kernel<<<gx, TG_THREADS, 0, st>>>(*L, sg);
+            const int cx = ceil_div(M, TG_BM) * ceil_div(L->seg[sg].C, TG_BN);
+            int zx = ceil_div(2 * 148, cx);
+            int nps = ceil_div(ceil_div(L->N, zx), TG_BK) * TG_BK;
+            if (nps < 2 * TG_BK) nps = 2 * TG_BK;
+            dim3 gx(ceil_div(M, TG_BM), ceil_div(L->seg[sg].C, TG_BN), ceil_div(L->N, nps));
+            train_dx_kernel<<<gx, TG_THREADS, 0, st>>>(*L, sg, nps);
             FCN_LAUNCH_CHECK();
         }
     }

@@ -261,7 +261,18 @@ class TrainEngine:
         self._table_host = arr
         self.table_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self._bn_counters = [b for n, b in model.named_buffers() if n.endswith("num_batches_tracked")]
+        # static inputs (the launch sequences are captured into CUDA graphs)
+        self.in_pc = torch.zeros((B, 3, N), dtype=f32, device=dev)
+        self.in_centers = [torch.zeros((B, 3, T[s]), dtype=f32, device=dev) for s in range(S)]
+        self.in_onehot = torch.zeros((B, max(self.V, 1)), dtype=f32, device=dev)
+        for P in self.pools:
+            P.one_hot = _ptr(self.in_onehot) if self.V > 0 else None
         self.group_args = self._group_args()
+        self._graphs = {}
+        self.use_graph = True
+        lib = _lib.load()
+        need = max([int(lib.fcn_train_workspace_floats(C.byref(L))) for L in self.layers] + [1])
+        self.workspace = torch.empty(need, dtype=f32, device=dev)   # K-split partial sums of the skinny FCN layers
 
     # ------------------------------------------------------------------
     def _group_args(self):
@@ -280,45 +291,31 @@ class TrainEngine:
             g.feat_pitch[s] = 0
         g.ntiles = _ptr(self.ntiles)
         g.force_scan = 0
+        g.pc, g.one_hot = _ptr(self.in_pc), None
+        for s in range(S):
+            g.centers[s] = _ptr(self.in_centers[s])
         return g
 
-    @torch.no_grad()
-    def forward(self, pc, centers, one_hot):
-        """-> (cls logits (B*T2, 2), reg logits (B*T2, out)) as views of the engine's buffers."""
+    # ---- launch sequences (all pointers are static: the step is CUDA-graph capturable)
+    def _seq_forward(self):
         S = len(self.T)
-        assert tuple(pc.shape) == (self.B, 3, self.N) and pc.is_contiguous() and pc.dtype == torch.float32
         st = _stream()
         torch._foreach_zero_(self._zero_fwd)
-        g = self.group_args
-        g.pc, g.one_hot = _ptr(pc), None
-        for s, c in enumerate(centers):
-            assert c.is_contiguous() and tuple(c.shape) == (self.B, 3, self.T[s])
-            g.centers[s] = _ptr(c)
-        _lib.call("fcn_group_rows", C.byref(g), st)
+        _lib.call("fcn_group_rows", C.byref(self.group_args), st)
         li = 0
         for s in range(S):
             for _ in range(3):
-                _lib.call("fcn_train_forward", C.byref(self.layers[li]), st)
+                _lib.call("fcn_train_forward", C.byref(self.layers[li]), _ptr(self.workspace), self.workspace.numel(), st)
                 li += 1
-            P = self.pools[s]
-            P.one_hot = _ptr(one_hot) if self.V > 0 else None
-            _lib.call("fcn_train_pool", C.byref(P), 0, st)
+            _lib.call("fcn_train_pool", C.byref(self.pools[s]), 0, st)
         while li < len(self.layers):
-            _lib.call("fcn_train_forward", C.byref(self.layers[li]), st)
+            _lib.call("fcn_train_forward", C.byref(self.layers[li]), _ptr(self.workspace), self.workspace.numel(), st)
             li += 1
-        return self.act["cls_out"]["Y"], self.act["reg_out"]["Y"]
 
-    @torch.no_grad()
-    def backward(self, dcls, dreg, update_running=True, stage="all"):
-        """dlogits -> gradients of every parameter, ACCUMULATED into the flat bucket ``self.flat.grad``.
-        stage = "fcn" (heads + ConvFeatNet: everything the feat_net gradients depend on), "pointnet" (the rest +
-        BN bookkeeping) or "all"."""
+    def _seq_backward(self, stage, update_running):
         st = _stream()
         S = len(self.T)
         if stage in ("all", "fcn"):
-            torch._foreach_zero_(self._zero_bwd)
-            self.act["cls_out"]["dA"].copy_(dcls.reshape(self.act["cls_out"]["dA"].shape))
-            self.act["reg_out"]["dA"].copy_(dreg.reshape(self.act["reg_out"]["dA"].shape))
             # FCN + heads in reverse creation order (a topological order of the backward graph: every consumer of
             # a tensor was created after it)
             for li in range(len(self.layers) - 1, self.n_pn_layers - 1, -1):
@@ -336,6 +333,58 @@ class TrainEngine:
             _lib.call("fcn_train_finalize", _ptr(self.table_dev), self.n_pn_layers, 1 if update_running else 0, st)
             if update_running and self._bn_counters:
                 torch._foreach_add_(self._bn_counters, 1)
+
+    def _graph(self, key, fn):
+        """Capture `fn` once (after an eager warm-up run, whose effects are the first execution) and replay it."""
+        g = self._graphs.get(key)
+        if g is None:
+            fn()                                   # eager: this call's work
+            try:
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                self._graphs[key] = g
+            except Exception as e:                 # stay functional without graphs
+                import sys
+                sys.stderr.write("TrainEngine: CUDA-graph capture of %r failed (%r); launching eagerly\n" % (key, e))
+                self._graphs[key] = False
+                torch.cuda.synchronize()
+            return
+        if g is False:
+            fn()
+        else:
+            g.replay()
+
+    @torch.no_grad()
+    def forward(self, pc, centers, one_hot):
+        """-> (cls logits (B*T2, 2), reg logits (B*T2, out)) as views of the engine's buffers."""
+        assert tuple(pc.shape) == (self.B, 3, self.N) and pc.dtype == torch.float32
+        self.in_pc.copy_(pc)
+        for s, c in enumerate(centers):
+            assert tuple(c.shape) == (self.B, 3, self.T[s])
+            self.in_centers[s].copy_(c)
+        if self.V > 0:
+            self.in_onehot.copy_(one_hot)
+        if self.use_graph:
+            self._graph("fwd", self._seq_forward)
+        else:
+            self._seq_forward()
+        return self.act["cls_out"]["Y"], self.act["reg_out"]["Y"]
+
+    @torch.no_grad()
+    def backward(self, dcls, dreg, update_running=True, stage="all"):
+        """dlogits -> gradients of every parameter, ACCUMULATED into the flat bucket ``self.flat.grad``.
+        stage = "fcn" (heads + ConvFeatNet: everything the feat_net gradients depend on), "pointnet" (the rest +
+        BN bookkeeping) or "all"."""
+        if stage in ("all", "fcn"):
+            torch._foreach_zero_(self._zero_bwd)
+            self.act["cls_out"]["dA"].copy_(dcls.reshape(self.act["cls_out"]["dA"].shape))
+            self.act["reg_out"]["dA"].copy_(dreg.reshape(self.act["reg_out"]["dA"].shape))
+        if self.use_graph:
+            self._graph(("bwd", stage, bool(update_running)), lambda: self._seq_backward(stage, update_running))
+        else:
+            self._seq_backward(stage, update_running)
 
     def kernel_launches_per_step(self):
         n_fwd = len(self.layers) + len(self.pools) + 2

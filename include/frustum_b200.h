@@ -298,7 +298,11 @@ typedef struct {
     const float *gamma, *beta;
     float *dgamma, *dbeta, *run_mean, *run_var;
 } fcn_train_layer;
-FCN_API int fcn_train_forward(const fcn_train_layer *layer, fcn_stream_t stream);
+/* `workspace` (may be NULL): scratch for the K-split of skinny layers (partial sums, added in a fixed order);
+ * fcn_train_workspace_floats(layer) = the size the launcher would like for this layer. */
+FCN_API long long fcn_train_workspace_floats(const fcn_train_layer *layer);
+FCN_API int fcn_train_forward(const fcn_train_layer *layer, float *workspace, long long workspace_floats,
+                              fcn_stream_t stream);
 /* backward of one layer: column reduction, dW (all segments), dX for the segments in need_dx_mask */
 FCN_API int fcn_train_backward(const fcn_train_layer *layer, int need_dx_mask, fcn_stream_t stream);
 /* PointNet pooling: feat[(b,t), c] = (cnt > 0) * max_k relu(bn(Y[(b,t,k), c])), one-hot columns appended
