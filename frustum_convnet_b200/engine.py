@@ -112,7 +112,9 @@ class FrustumEngine:
         # a producer tile holds its SM idle: FEW CTAs per forward and several forwards in flight maximise
         # throughput (measured, B=32 car, 8 streams: 24 CTAs 275 k frustums/s, 148 CTAs 121 k); FCN_MEGA_GRID=148
         # minimises the latency of a single forward instead (0.32 ms vs 0.37 ms)
-        self.mega_grid = int(os.environ.get("FCN_MEGA_GRID", "24"))
+        # 0 = adaptive: 2/3 of the smallest per-layer tile count of the main chain, within [4, 48] (car B=32: 24,
+        # people: 48, SUN-RGBD: 6 - measured optima 24 / 32-48 / 6-8)
+        self.mega_grid = int(os.environ.get("FCN_MEGA_GRID", "0"))
         self.tile_rows = 64 if self.precision == 0 else 128
         self.out_size = reg_out_size(dataset, self.num_bins)
         self.ld_logit = _round_up(2 + self.out_size, 64)
@@ -427,6 +429,7 @@ class _Plan:
             self.conv_args.append(a)
 
         self.mega_args = None
+        self.mega_grid = 0
         if eng.use_mega and eng.has_heads and all(a.precision in (3, 4) for a in self.conv_args):
             self._build_mega()
 
@@ -466,7 +469,12 @@ class _Plan:
         self._mega_dev = torch.frombuffer(bytearray(bytes(JA)), dtype=torch.uint8).to(dev)
         self.mega_sync = torch.zeros(4 + nflags, dtype=torch.int32, device=dev)
         m = _lib.MegaArgs()
-        m.n_layers, m.n_jobs, m.n_flags, m.grid = len(descs), len(jobs), nflags, eng.mega_grid
+        grid = eng.mega_grid
+        if grid <= 0:
+            chain = [d.m_tiles * d.n_tiles for d in descs if not d.name.endswith("_deconv") and d.name != "heads"]
+            grid = max(4, min(48, (2 * min(chain)) // 3))
+        self.mega_grid = grid
+        m.n_layers, m.n_jobs, m.n_flags, m.grid = len(descs), len(jobs), nflags, grid
         m.tmaps, m.n_maps = C.addressof(maps), len(map_keys)
         m.layers, m.jobs = C.addressof(LA), _ptr(self._mega_dev)
         m.sync = _ptr(self.mega_sync)
