@@ -242,10 +242,10 @@ class FrustumEngine:
     # ------------------------------------------------------------------ public calls
     @torch.no_grad()
     def forward(self, pc: torch.Tensor, centers: Sequence[torch.Tensor], one_hot, use_graph=False,
-                copy_out=True):
-        """Eval forward -> the 6-tuple of det_base.py:411."""
+                copy_out=True, trusted=False):
+        """Eval forward -> the 6-tuple of det_base.py:411.  trusted: the caller validated these tensors before."""
         p = self.plan(pc.shape[0], pc.shape[2], [c.shape[2] for c in centers])
-        return p.run(pc, centers, one_hot, use_graph=use_graph, copy_out=copy_out)
+        return p.run(pc, centers, one_hot, use_graph=use_graph, copy_out=copy_out, trusted=trusted)
 
     @torch.no_grad()
     def pointnet_feat(self, pc, centers, one_hot):
@@ -664,15 +664,15 @@ class _Plan:
             off += o.numel()
         return tuple(outs)
 
-    def run(self, pc, centers, one_hot, use_graph=False, copy_out=True):
+    def run(self, pc, centers, one_hot, use_graph=False, copy_out=True, trusted=False):
         """copy_out=True returns fresh tensors (reference semantics); False returns views of the
         plan's output block, which the next call overwrites (zero-copy serving / benchmarking)."""
-        out = self._run(pc, centers, one_hot, use_graph)
+        out = self._run(pc, centers, one_hot, use_graph, trusted)
         return self._views(self.out_flat.clone()) if copy_out else out
 
-    def _run(self, pc, centers, one_hot, use_graph=False):
+    def _run(self, pc, centers, one_hot, use_graph=False, trusted=False):
         own = use_graph and pc.data_ptr() == self.in_flat.data_ptr()   # the plan's own input views: valid by construction
-        if not own:
+        if not own and not trusted:
             self._check_inputs(pc, centers, one_hot)
         dev = self.eng.device
         if dev.index is not None and torch.cuda.current_device() != dev.index:
