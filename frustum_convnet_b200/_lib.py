@@ -143,6 +143,15 @@ class TrainPool(C.Structure):
                 ("dfeat", C.c_void_p), ("dA", C.c_void_p)]
 
 
+class InputArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("N", C.c_int), ("num_scales", C.c_int), ("num_classes", C.c_int),
+                ("T", C.c_int * MAX_SCALES), ("stride", C.c_double * MAX_SCALES),
+                ("points", C.c_void_p), ("point_offsets", C.c_void_p), ("choice", C.c_void_p),
+                ("frustum_angle", C.c_void_p), ("box2d", C.c_void_p), ("P", C.c_void_p), ("cls_index", C.c_void_p),
+                ("point_cloud", C.c_void_p), ("centers", C.c_void_p * MAX_SCALES), ("one_hot", C.c_void_p),
+                ("rot_angle", C.c_void_p)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
 _I, _F, _P = C.c_int, C.c_float, C.c_void_p
 SIGNATURES = {
@@ -166,6 +175,9 @@ SIGNATURES = {
     "fcn_train_pool": (_I, [C.POINTER(TrainPool), _I, _P]),
     "fcn_train_finalize": (_I, [_P, _I, _I, _P]),
     "fcn_adam_step": (_I, [_P, _P, _P, _P, C.c_longlong, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "fcn_rotate_nms_3d": (_I, [_I, _P, _P, _F, _I, _P, _P, _I, _P]),
+    "fcn_rotate_nms_3d_max_dets": (_I, []),
+    "fcn_build_inputs": (_I, [C.POINTER(InputArgs), _P]),
     "fcn_ipc_export": (_I, [_P, _P, C.POINTER(C.c_longlong)]),
     "fcn_ipc_open": (_I, [_P, C.POINTER(C.c_void_p)]),
     "fcn_ipc_close": (_I, [_P]),

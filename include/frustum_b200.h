@@ -329,6 +329,46 @@ FCN_API int fcn_adam_step(float *param, const float *grad, float *exp_avg, float
                           float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                           fcn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (8) Inference post-processing ("next" row 8(f)-4): batched rotated 3-D NMS on the device.  Replaces
+ *     `cube_nms` = rotate_nms_3d_cc (ops/pybind11/rbbox_iou.py:294-311) -> rotate_non_max_suppression_3d_cpu
+ *     (ops/pybind11/nms_cpu.h:148-240), called per image and class from train/test_net_det.py:126-152.
+ *     dets: (total, 8) fp32 rows [cx, cy, cz, l, w, h, ry, score]; segment s = rows
+ *     [seg_offsets[s], seg_offsets[s+1]) (one image x class list, at most fcn_rotate_nms_3d_max_dets() rows are
+ *     considered); keep: (num_segments, keep_stride) int32 GLOBAL row indices in descending-score order,
+ *     keep_count[s] <= top_k of them are valid.  A box is suppressed by a kept, higher-scored box when their
+ *     axis-aligned bounding cubes overlap and the rotated 3-D IoU is >= thresh.
+ * ------------------------------------------------------------------------------------------ */
+FCN_API int fcn_rotate_nms_3d(int num_segments, const float *dets, const int32_t *seg_offsets, float thresh, int top_k,
+                              int32_t *keep, int32_t *keep_count, int keep_stride, fcn_stream_t stream);
+FCN_API int fcn_rotate_nms_3d_max_dets(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (9) Device-side input builder ("next" row 8(f)-3): ProviderDataset.__getitem__ of datasets/provider_sample.py
+ *     (:133-203 resample + centre-view rotation, :291-327 generate_ref, datasets/data_utils.py:7-21,73-93) for a
+ *     whole batch in one launch, from raw frustum points that stay resident in HBM.  `choice` (B,N) int32 = the
+ *     caller's np.random.choice draw (indices into each frustum's own points).  float64 arithmetic with the
+ *     reference's float32 casts.  Outputs have the layouts the model consumes: point_cloud (B,3,N),
+ *     centers[s] (B,3,T_s), one_hot (B,num_classes) (optional), rot_angle (B) (optional).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int B, N, num_scales, num_classes;
+    int T[FCN_MAX_SCALES];
+    double stride[FCN_MAX_SCALES];
+    const float *points;          /* (sum n_b, 3) raw frustum points, rect camera coordinates */
+    const int32_t *point_offsets; /* (B+1) */
+    const int32_t *choice;        /* (B, N) */
+    const double *frustum_angle;  /* (B) */
+    const double *box2d;          /* (B, 4) x1, y1, x2, y2 */
+    const double *P;              /* (B, 12) calib P2, row-major 3x4 */
+    const int32_t *cls_index;     /* (B) or NULL */
+    float *point_cloud;
+    float *centers[FCN_MAX_SCALES];
+    float *one_hot;               /* or NULL */
+    float *rot_angle;             /* or NULL */
+} fcn_input_args;
+FCN_API int fcn_build_inputs(const fcn_input_args *args, fcn_stream_t stream);
+
 /* Layout helpers for the channel-first module APIs: (B,C,T) <-> (B,pitch >= T,ld) position-major. */
 FCN_API int fcn_bct_to_btc(int B, int C, int T, int pitch, int ld, const float *src, float *dst,
                            fcn_stream_t stream);
