@@ -383,8 +383,36 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
                 if (dbg) dbg[12] = clock64();
                 if (row_ok)
                     decode_row(L.out + ((size_t)b * L.P_store + rt) * L.ld_out, b * p.T + rt, b, rt, p.T, p.NH, p.NS,
-                               p.center_ref, p.mean_size, (const DecodeOut *)p.outs, p.n_out);
-                if (p.n_out > 1) __threadfence_system();   // remote (NVLink) stores before the completion count
+                               p.center_ref, p.mean_size, (const DecodeOut *)p.outs, 1);
+                if (p.n_out > 1) {
+                    // Multi-GPU: replicate this tile's decoded rows into the peers' gather buffers.  The valid rows
+                    // of a tile are ONE contiguous range of output rows (pad rows have no output row), so each of
+                    // the six arrays is a contiguous run: copied with consecutive threads -> consecutive floats
+                    // (full 128-byte NVLink write packets; per-row scattered 4-byte remote stores measured +11 %
+                    // step time at 8 GPUs).
+                    __threadfence();
+                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                    const int rfirst = m_tile * MG_ROWS, rlast = min(rfirst + MG_ROWS, L.n_rows) - 1;
+                    int b0 = rfirst / L.P_m, t0 = rfirst - b0 * L.P_m;
+                    if (t0 >= L.T_out) { ++b0; t0 = 0; }
+                    int b1 = rlast / L.P_m, t1 = rlast - b1 * L.P_m;
+                    if (t1 >= L.T_out) t1 = L.T_out - 1;
+                    const int R_lo = b0 * p.T + t0, R_hi = b1 * p.T + t1 + 1;     // [R_lo, R_hi) output rows
+                    if (R_hi > R_lo && b0 < p.B) {
+                        const int widths[6] = {2, 3, 1, 3, p.NH, p.NS};
+                        const float *const *loc = (const float *const *)&p.outs[0];
+#pragma unroll 1
+                        for (int a6 = 0; a6 < 6; ++a6) {
+                            const size_t base = (size_t)R_lo * widths[a6];
+                            const int nflt = (R_hi - R_lo) * widths[a6];
+                            for (int i = etid; i < nflt; i += 128) {
+                                const float v = loc[a6][base + i];
+                                for (int o = 1; o < p.n_out; ++o) ((float *const *)&p.outs[o])[a6][base + i] = v;
+                            }
+                        }
+                    }
+                    __threadfence_system();                // remote (NVLink) stores before the completion count
+                }
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) red_release_gpu_add(flags + L.flag_base + m_tile, 1);
