@@ -143,6 +143,18 @@ class TrainPool(C.Structure):
                 ("dfeat", C.c_void_p), ("dA", C.c_void_p)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("T2", C.c_int), ("NH", C.c_int), ("NS", C.c_int), ("with_iou", C.c_int),
+                ("reserved0", C.c_int),
+                ("cls", C.c_void_p), ("reg", C.c_void_p), ("center_ref2", C.c_void_p),
+                ("cls_label", C.c_void_p), ("size_class", C.c_void_p),
+                ("box3d_center", C.c_void_p), ("box3d_heading", C.c_void_p), ("box3d_size", C.c_void_p),
+                ("mean_size", C.c_void_p),
+                ("w_box", C.c_float), ("w_head_reg", C.c_float), ("w_size_reg", C.c_float), ("w_corner", C.c_float),
+                ("iou_thresh", C.c_float), ("reserved1", C.c_float),
+                ("dcls", C.c_void_p), ("dreg", C.c_void_p), ("out", C.c_void_p), ("scratch", C.c_void_p)]
+
+
 class InputArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("N", C.c_int), ("num_scales", C.c_int), ("num_classes", C.c_int),
                 ("T", C.c_int * MAX_SCALES), ("stride", C.c_double * MAX_SCALES),
@@ -177,6 +189,7 @@ SIGNATURES = {
     "fcn_adam_step": (_I, [_P, _P, _P, _P, C.c_longlong, _F, _F, _F, _F, _F, _I, _F, _P]),
     "fcn_rotate_nms_3d": (_I, [_I, _P, _P, _F, _I, _P, _P, _I, _P]),
     "fcn_rotate_nms_3d_max_dets": (_I, []),
+    "fcn_det_loss": (_I, [C.POINTER(LossArgs), _P]),
     "fcn_build_inputs": (_I, [C.POINTER(InputArgs), _P]),
     "fcn_ipc_export": (_I, [_P, _P, C.POINTER(C.c_longlong)]),
     "fcn_ipc_open": (_I, [_P, C.POINTER(C.c_void_p)]),

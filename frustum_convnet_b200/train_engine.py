@@ -407,7 +407,9 @@ class TrainStep:
         self._comm = None
         self._split = 0
         self._loss_graphs = {}
-        self.use_loss_graph = True     # losses + their backward as one CUDA graph (train_path.LossGraph)
+        # losses + d/dlogits: "kernel" = fused hand-written kernels (csrc/loss.cu), "graph" = the PyTorch ops as one
+        # CUDA graph (train_path.LossGraph), "eager" = the reference-shaped PyTorch ops
+        self.loss_impl = "kernel"
 
     def engine(self, B, N, T) -> TrainEngine:
         key = (int(B), int(N), tuple(int(t) for t in T))
@@ -422,12 +424,13 @@ class TrainStep:
 
     def _losses(self, eng, cls, reg, center_ref2, data):
         """-> (losses, metrics, dcls, dreg)."""
-        from .train_path import LossGraph, losses_from_logits
-        if self.use_loss_graph:
-            key = (eng.B, eng.T2)
+        from .train_path import FusedLoss, LossGraph, losses_from_logits
+        if self.loss_impl in ("kernel", "graph"):
+            key = (self.loss_impl, eng.B, eng.T2)
             lg = self._loss_graphs.get(key)
             if lg is None:
-                lg = self._loss_graphs[key] = LossGraph(self.model, eng.B, eng.T2, reg.shape[1], cls.device)
+                cls_ = FusedLoss if self.loss_impl == "kernel" else LossGraph
+                lg = self._loss_graphs[key] = cls_(self.model, eng.B, eng.T2, reg.shape[1], cls.device)
             return lg.run(cls, reg, center_ref2, data)
         cls_l = cls.detach().clone().requires_grad_(True)
         reg_l = reg.detach().clone().requires_grad_(True)

@@ -330,6 +330,27 @@ FCN_API int fcn_adam_step(float *param, const float *grad, float *exp_avg, float
                           fcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (7b) Fused detection losses + gradient w.r.t. the head logits (row 8(f)-2, train half): everything of
+ *      models/det_base.py:414-503 after the heads - foreground selection, focal loss (models/common.py:217-232),
+ *      Huber / cross-entropy / corner losses (models/model_util.py:9-72, models/box_transform.py:5-65), accuracies
+ *      and the rotated-IoU metrics - and its autograd backward, in three tiny launches.
+ *      cls (B*T2, 2), reg (B*T2, 3 + 2*NH + 4*NS) rows in (frustum, position) order; labels as the reference's
+ *      data dict holds them (cls_label int64 (B,T2) in {-1,0,1}, size_class int64 (B), box3d_* fp32).
+ *      out[0..7] = total, cls, center, head_cls, head_res, size_cls, size_res, corners; out[8..13] = cls_acc,
+ *      head_acc, size_acc, IoU_2D, IoU_3D, IoU_>=thresh; out[14..15] = #foreground, #non-ignored rows.
+ *      scratch: 16 floats.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int B, T2, NH, NS, with_iou, reserved0;
+    const float *cls, *reg, *center_ref2 /* (B,3,T2) */;
+    const long long *cls_label, *size_class;
+    const float *box3d_center, *box3d_heading, *box3d_size, *mean_size /* (NS,3) */;
+    float w_box, w_head_reg, w_size_reg, w_corner, iou_thresh, reserved1;
+    float *dcls, *dreg, *out /* 16 floats */, *scratch /* 16 floats */;
+} fcn_loss_args;
+FCN_API int fcn_det_loss(const fcn_loss_args *args, fcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * (8) Inference post-processing ("next" row 8(f)-4): batched rotated 3-D NMS on the device.  Replaces
  *     `cube_nms` = rotate_nms_3d_cc (ops/pybind11/rbbox_iou.py:294-311) -> rotate_non_max_suppression_3d_cpu
  *     (ops/pybind11/nms_cpu.h:148-240), called per image and class from train/test_net_det.py:126-152.
