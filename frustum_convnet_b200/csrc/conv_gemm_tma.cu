@@ -21,16 +21,9 @@ using namespace umma;
 constexpr int GM_ROWS = 128;
 constexpr int GM_THREADS = 6 * 32;   // warp 0: TMA producer, warp 1: MMA, warps 2-5: epilogue
 
-// A/B knob (scripts/next_round_ab.sh): stage count of the 128-wide N tile.  3 stages = 193 KB per CTA (nothing
-// else fits on the SM); 2 stages = 129 KB, which lets a conv CTA share an SM with a 64-channel PointNet CTA
-// (87 KB) of another in-flight forward at the price of a shallower K pipeline.
-#ifndef FCN_GM_NSTAGE
-#define FCN_GM_NSTAGE 3
-#endif
-
 template <int NT>
 struct GmCfg {
-    static constexpr int NSTAGE = NT > 64 ? FCN_GM_NSTAGE : 4;
+    static constexpr int NSTAGE = NT > 64 ? 3 : 4;
     static constexpr int A_ATOM = GM_ROWS * 128, W_ATOM = NT * 128;
     static constexpr int A_STAGE = 2 * A_ATOM, W_STAGE = 2 * W_ATOM;
     static constexpr int OFF_W = NSTAGE * A_STAGE;

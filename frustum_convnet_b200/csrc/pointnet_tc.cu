@@ -256,29 +256,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
             // ---- layer 1 (fp32 FMA) -> A1, K-blocks kb = h, h+2, ...
             for (int kb = h; kb < Cfg::KB1; kb += 2) {
                 uint8_t *dst = sA + kb * (TC_ROWS * 128) + row_off;
-#if FCN_SIMT_PREFETCH
-                // the compiler cannot prove that the weight loads do not alias the A-tile stores, so it keeps
-                // every batch's LDS behind the previous batch's STS; loading one batch ahead by hand takes the
-                // LDS latency off the per-batch dependency chain
-                float4 wn[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wn[j] = w1s[kb * 32 + j];
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    float4 w[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) w[j] = wn[j];
-                    if (c4 < 7) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) wn[j] = w1s[kb * 32 + (c4 + 1) * 4 + j];
-                    }
-                    float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        o[j] = to_tf32(fmaxf(fmaf(rec.z, w[j].z, fmaf(rec.y, w[j].y, fmaf(rec.x, w[j].x, w[j].w))), 0.f));
-                    *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-                }
-#else
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     float o[4];
@@ -289,7 +266,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                     }
                     *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                 }
-#endif
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[kb]);
@@ -304,20 +280,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 tmem_ld32(lane_taddr + kb * 32, v);
                 tmem_wait_ld();
                 uint8_t *dst = sA + kb * (TC_ROWS * 128) + row_off;
-#if FCN_SIMT_PREFETCH
-                float4 bq[8];                          // all 32 biases of the K block before the first store
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) bq[c4] = *(const float4 *)(b2s + kb * 32 + c4 * 4);
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    float4 o;
-                    o.x = to_tf32(fmaxf(__uint_as_float(v[c4 * 4 + 0]) + bq[c4].x, 0.f));
-                    o.y = to_tf32(fmaxf(__uint_as_float(v[c4 * 4 + 1]) + bq[c4].y, 0.f));
-                    o.z = to_tf32(fmaxf(__uint_as_float(v[c4 * 4 + 2]) + bq[c4].z, 0.f));
-                    o.w = to_tf32(fmaxf(__uint_as_float(v[c4 * 4 + 3]) + bq[c4].w, 0.f));
-                    *(float4 *)(dst + ((c4 ^ rx) << 4)) = o;
-                }
-#else
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     float o[4];
@@ -326,7 +288,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         o[j] = to_tf32(fmaxf(__uint_as_float(v[c4 * 4 + j]) + b2s[kb * 32 + c4 * 4 + j], 0.f));
                     *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                 }
-#endif
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();

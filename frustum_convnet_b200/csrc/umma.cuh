@@ -10,14 +10,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-// A/B knob (scripts/next_round_ab.sh): hand-pipelined shared-memory loads in the SIMT phases of the PointNet
-// kernels (layer 1 weights, epilogue-2 biases).  Same arithmetic, different instruction order.
-#ifndef FCN_SIMT_PREFETCH
-#define FCN_SIMT_PREFETCH 0
-#endif
-// A/B knob: persistent PointNet kernels use only as many CTAs (clusters) as their number of rounds needs.
+// Persistent PointNet kernels use only as many CTAs (clusters) as their number of rounds needs: the kernel takes the
+// same ceil(n / slots) rounds, but the SMs it does not need go to the other kernels in flight (measured, car B=32,
+// 8 streams: 283.0 k vs 279.3 k frustums/s; the round-1 candidates "hand-pipelined SIMT loads", "5 weight stages in
+// the 2-CTA kernel" and "late PDL trigger" measured within +-1 % and were dropped).
 #ifndef FCN_BALANCE_ROUNDS
-#define FCN_BALANCE_ROUNDS 0
+#define FCN_BALANCE_ROUNDS 1
 #endif
 
 namespace fcn {
