@@ -8,8 +8,11 @@
 // the per-CTA weight bytes (each CTA stages half of the N rows of every weight tile), which makes room for
 // N = 256 instructions (128 clk of math each) in the same 16 KB stage slots.
 //
-// Per tile pair:   L1 (fp32 FMA, both CTAs) -> A1 | L2: D2[256 x C2] (TMEM region R0) | epilogue 2 -> A2 |
-//                  L3: chunk 0 -> R1, chunk 1 -> R0 (aliasing the drained layer-2 accumulator) | epilogue 3.
+// Per tile pair:   L1 (fp32 FMA, both CTAs) -> A1 | L2: D2[256 x C2] (TMEM region Ra) | epilogue 2 -> A2 |
+//                  L3: chunk 0 -> Rb, chunk 1 -> Ra (aliasing the drained layer-2 accumulator) | epilogue 3.
+// With two layer-3 chunks the regions swap roles every pair (Ra = R0, R1, R0, ...): the next pair's layer 2 goes to
+// the region whose chunk-0 result was drained long ago, so the compute warps run  L1(next pair) BEFORE the chunk-1
+// epilogue of this pair and that epilogue (and its atomics) hides behind the next pair's layer-2 MMAs.
 // Cross-CTA protocol: the leader CTA (cluster rank 0) issues every MMA; both CTAs' compute warps arrive on
 // the leader's A-ready / region-empty mbarriers (remote arrive through mapa), the peer relays "my half of
 // the weight stage landed" to the leader's stage barrier, and the leader's tcgen05.commit multicasts
@@ -21,7 +24,7 @@ namespace fcn {
 using namespace umma;
 
 constexpr int T2_ROWS = 128;
-constexpr int T2_COMPUTE_WARPS = 8;
+constexpr int T2_COMPUTE_WARPS = 16;         // 4 per TMEM lane quadrant: the epilogues are latency-bound, not issue-bound
 constexpr int T2_THREADS = (T2_COMPUTE_WARPS + 2) * 32;
 constexpr int T2_STAGE_BYTES = 16384;          // per CTA: half of a [256 x 128 B] weight tile
 
@@ -42,7 +45,7 @@ struct Tc2Cfg {
     static constexpr int OFF_B3 = OFF_B2 + C2 * 4;
     static constexpr int OFF_SECT = OFF_B3 + C3 * 4;
     static constexpr int OFF_BAR = OFF_SECT + 2 * 2 * T2_ROWS * 4;   // int sect[parity][tile of the pair][128]
-    static constexpr int NBAR = 2 * NSTAGE + 2 * KBMAX + 1 + 2 + 2;
+    static constexpr int NBAR = 2 * NSTAGE + 3 * KBMAX + 1 + 2 + 2;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int BYTES = OFF_TMEM + 16 + 1024;
     static_assert(C1 == C2 && C2 <= 256 && C3 % 256 == 0 && NCH3 <= 2, "supported shapes");
@@ -103,9 +106,10 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
     int *sect_all = (int *)(smem + Cfg::OFF_SECT);
     uint64_t *bars = (uint64_t *)(smem + Cfg::OFF_BAR);
     uint64_t *w_full = bars, *w_empty = bars + Cfg::NSTAGE;
-    uint64_t *a1_ready = bars + 2 * Cfg::NSTAGE;          // leader only, 8 arrivals (4 warps x 2 CTAs)
+    uint64_t *a1_ready = bars + 2 * Cfg::NSTAGE;          // leader only, one arrival per compute warp of both CTAs
     uint64_t *a2_ready = a1_ready + Cfg::KBMAX;
-    uint64_t *acc2_full = a2_ready + Cfg::KBMAX;          // both CTAs, multicast commit
+    uint64_t *a_free = a2_ready + Cfg::KBMAX;             // both CTAs, multicast commit: last chunk's MMAs read A2[kb]
+    uint64_t *acc2_full = a_free + Cfg::KBMAX;            // both CTAs, multicast commit
     uint64_t *acc3_full = acc2_full + 1;                  // [2] per chunk, both CTAs
     uint64_t *r_empty = acc3_full + 2;                    // [2] TMEM regions, leader only, 16 arrivals
     uint32_t *tmem_slot = (uint32_t *)(smem + Cfg::OFF_TMEM);
@@ -130,7 +134,11 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             mbar_init(&w_full[i], rank == 0 ? 2 : 1);      // own loader (+tx bytes) [+ the peer's relay]
             mbar_init(&w_empty[i], 1);
         }
-        for (int i = 0; i < Cfg::KBMAX; ++i) { mbar_init(&a1_ready[i], 8); mbar_init(&a2_ready[i], 8); }
+        for (int i = 0; i < Cfg::KBMAX; ++i) {
+            mbar_init(&a1_ready[i], 2 * T2_COMPUTE_WARPS);
+            mbar_init(&a2_ready[i], 2 * T2_COMPUTE_WARPS);
+            mbar_init(&a_free[i], 1);
+        }
         mbar_init(acc2_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc3_full[i], 1); mbar_init(&r_empty[i], 2 * T2_COMPUTE_WARPS); }
         fence_barrier_init();
@@ -189,8 +197,9 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             const bool dbg = p.dbg_clocks != nullptr && blockIdx.x == 0 && lane == 0;
             for (int it = 0; it < my_pairs; ++it) {
                 const uint32_t par = it & 1;
-                // ---- layer 2 -> region R0 (columns [0, C2))
-                if (Cfg::NCH3 == 2) mbar_wait(&r_empty[0], par ^ 1);   // chunk-1 epilogue of the previous pair
+                const uint32_t ra = Cfg::NCH3 == 2 ? par : 0u, rb = ra ^ 1u;   // TMEM regions of this pair (x 256 columns)
+                // ---- layer 2 -> region Ra (drained by the chunk-0 epilogue of the previous pair)
+                if (Cfg::NCH3 == 2) mbar_wait(&r_empty[ra], par ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < Cfg::KB1; ++kb, ++job) {
                     const uint32_t st = job % Cfg::NSTAGE, ph = (job / Cfg::NSTAGE) & 1;
@@ -206,7 +215,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                         const uint64_t bd = bdesc0 + (uint64_t)(st * (T2_STAGE_BYTES >> 4));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            mma_tf32_2cta(tmem_base, ad + 2 * k, bd + 2 * k, idesc2, (kb | k) != 0);
+                            mma_tf32_2cta(tmem_base + ra * 256u, ad + 2 * k, bd + 2 * k, idesc2, (kb | k) != 0);
                         mma_commit_2cta(&w_empty[st]);
                     }
                     __syncwarp();
@@ -214,11 +223,12 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
                 if (t2_elect_one()) mma_commit_2cta(acc2_full);
                 __syncwarp();
-                // ---- layer 3: chunk 0 -> R1 (columns [256,512)), chunk 1 -> R0 (drained layer-2 accumulator)
+                // ---- layer 3: chunk 0 -> Rb (drained by the LAST epilogue of the previous pair), chunk 1 -> Ra (the
+                //      layer-2 accumulator, drained by epilogue 2: every a2_ready was waited for during chunk 0)
                 for (int nc = 0; nc < Cfg::NCH3; ++nc) {
-                    if (nc == 0) mbar_wait(&r_empty[1], par ^ 1);
+                    if (nc == 0) mbar_wait(&r_empty[rb], par ^ 1);
                     tc_fence_after();
-                    const uint32_t dcol = nc == 0 ? 256u : 0u;
+                    const uint32_t dcol = (nc == 0 ? rb : ra) * 256u;
                     for (int kb = 0; kb < Cfg::KB2; ++kb, ++job) {
                         const uint32_t st = job % Cfg::NSTAGE, ph = (job / Cfg::NSTAGE) & 1;
                         long long t0 = 0, t1 = 0, t2 = 0;
@@ -235,6 +245,7 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                             for (int k = 0; k < 4; ++k)   // transposed: M = 256 channels (W3), N = 2 x 128 rows (A2)
                                 mma_tf32_2cta(tmem_base + dcol, bd + 2 * k, ad + 2 * k, idesc3, (kb | k) != 0);
                             mma_commit_2cta(&w_empty[st]);
+                            if (nc == Cfg::NCH3 - 1) mma_commit_2cta(&a_free[kb]);   // A2[kb] may be refilled
                         }
                         __syncwarp();
                         if (dbg && job < 1000) { long long *d = p.dbg_clocks + 4 * job; d[0] = t0; d[1] = t1; d[2] = t2; d[3] = clock64(); }
@@ -247,47 +258,49 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
         pdl_launch_dependents_late();   // both CTAs: every MMA of this pair is issued / relayed
     } else {
         // ================= compute / epilogue warps (both CTAs, own 128-row tile) =================
-        const int q = warp & 3, h = warp >> 2;
+        // warp = q + 4 * grp: q = TMEM lane quadrant (rows 32q.. of the tile / channels 32q.. of the transposed layer 3),
+        // grp = 0..3 splits the K blocks (layer 1, epilogue 2) and, as (h, g) = (grp & 1, grp >> 1), the columns of the
+        // transposed accumulator (epilogue 3: rows [64g, 64g + 64) of tile h)
+        const int q = warp & 3, grp = warp >> 2, h = grp & 1, g = grp >> 1;
         const int row = q * 32 + lane;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const int rx = row & 7;
         auto tile_of = [&](int it, uint32_t r) -> int4 {
             const int tile = 2 * (cluster_id + it * nclusters) + (int)r;
-            return tile < ntiles ? tiles[tile] : make_int4(0, 0, 0, 0);   // odd tile count: empty partner tile
+            return (it < my_pairs && tile < ntiles) ? tiles[tile] : make_int4(0, 0, 0, 0);   // odd count: empty partner
         };
-        // h == 0 warps stage the records of this CTA's tile (layer 1), h == 1 warps the section ids of the
+        // g == 0 warps stage: h == 0 the records of this CTA's tile (layer 1), h == 1 the section ids of the
         // partner's tile (epilogue 3 drains BOTH tiles' rows for this CTA's half of the channels)
         auto rec_of = [&](const int4 &t) -> float4 {
-            return row < t.z ? ((const float4 *)p.rows + (size_t)t.x * p.row_cap + t.y)[row]
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            return (g == 0 && row < t.z) ? ((const float4 *)p.rows + (size_t)t.x * p.row_cap + t.y)[row]
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        int4 td_next = tile_of(0, rank), tdp_next = tile_of(0, rank ^ 1u);
-        float4 rec_next = rec_of(h == 0 ? td_next : tdp_next);
         const bool dbgc = p.dbg_clocks != nullptr && blockIdx.x == 0 && tid == 0;
-        for (int it = 0; it < my_pairs; ++it) {
-            const uint32_t par = it & 1;
-            long long *dc = p.dbg_clocks + 4096 + 16 * it;
-            if (dbgc) dc[0] = clock64();
-            const int4 td = td_next, tdp = tdp_next;
+        int4 td = tile_of(0, rank), tdp = tile_of(0, rank ^ 1u);     // own tile / partner's tile of the staged pair
+        float4 rec_pre = rec_of(h == 0 ? td : tdp);
+        // records + section ids of pair `it` (prefetched in td / tdp / rec_pre) into the parity buffers, then
+        // layer 1 (fp32 FMA) -> A1.  `chase`: A2[kb] of the previous pair is still being read by its last MMAs.
+        auto stage_and_layer1 = [&](int it, bool chase) {
             float4 *recs = recs_all + (it & 1) * T2_ROWS;
-            int *sect_s = sect_all + (it & 1) * (2 * T2_ROWS);   // [tile of the pair][row]
-            float4 rec = rec_next;
-            if (h == 0) recs[row] = rec;
-            sect_s[((h == 0) ? rank : (rank ^ 1u)) * T2_ROWS + row] = __float_as_int(rec.w) & 0x7fffffff;
-            if (it + 1 < my_pairs) {
-                td_next = tile_of(it + 1, rank);
-                tdp_next = tile_of(it + 1, rank ^ 1u);
-                rec_next = rec_of(h == 0 ? td_next : tdp_next);
+            int *sect_w = sect_all + (it & 1) * (2 * T2_ROWS);   // [tile of the pair][row]
+            // a_free[0] of the previous pair: its last chunk has started, i.e. EVERY warp has finished the epilogue-3
+            // pass that read this parity's section ids
+            if (chase) mbar_wait(&a_free[0], (it & 1) ^ 1);
+            if (g == 0) {
+                if (h == 0) recs[row] = rec_pre;
+                sect_w[((h == 0) ? rank : (rank ^ 1u)) * T2_ROWS + row] = __float_as_int(rec_pre.w) & 0x7fffffff;
             }
             asm volatile("bar.sync 1, %0;\n" ::"n"(T2_COMPUTE_WARPS * 32));
-            rec = recs[row];
-
-            // ---- layer 1 (fp32 FMA) -> A1
-            for (int kb = h; kb < Cfg::KB1; kb += 2) {
+            const float4 rec = recs[row];
+            // every warp computes ITS 8 channels (two 16-byte units) of every K block, in the order the MMAs consume
+            // them: a K block is complete ~1/4 of a block time after its buffer slice is free
+            for (int kb = 0; kb < Cfg::KB1; ++kb) {
+                if (chase) mbar_wait(&a_free[kb], (it & 1) ^ 1);
                 uint8_t *dst = sA + kb * (T2_ROWS * 128) + row_off;
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
+                for (int u = 0; u < 2; ++u) {
+                    const int c4 = 2 * grp + u;
                     float o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -300,42 +313,70 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&a1_ready[kb], 0);
             }
-            // ---- epilogue 2: TMEM R0 -> +bias, ReLU, TF32 -> A2 (same buffer)
-            if (dbgc) dc[2] = clock64();
+        };
+        stage_and_layer1(0, false);
+        for (int it = 0; it < my_pairs; ++it) {
+            const uint32_t par = it & 1;
+            const uint32_t ra = Cfg::NCH3 == 2 ? par : 0u, rb = ra ^ 1u;
+            long long *dc = p.dbg_clocks + 4096 + 16 * it;
+            if (dbgc) dc[0] = clock64();
+            const int *sect_s = sect_all + (it & 1) * (2 * T2_ROWS);
+            // epilogue 3 drains, per warp, rows of tile h of the pair: keep that tile's record, then prefetch the next
+            // pair's (its global loads fly during epilogue 2)
+            const int4 tdt = ((uint32_t)h == rank) ? td : tdp;
+            td = tile_of(it + 1, rank);
+            tdp = tile_of(it + 1, rank ^ 1u);
+            rec_pre = rec_of(h == 0 ? td : tdp);
+            // ---- epilogue 2: TMEM Ra -> +bias, ReLU, TF32 -> A2 (same buffer)
             mbar_wait(acc2_full, par);
             if (dbgc) dc[3] = clock64();
             tc_fence_after();
-            for (int kb = h; kb < Cfg::KB2; kb += 2) {
+            // every warp converts ITS 8 columns of every K block (four blocks per TMEM load batch)
+#pragma unroll 1
+            for (int kb0 = 0; kb0 < Cfg::KB2; kb0 += 4) {
                 uint32_t v[32];
-                tmem_ld32(lane_taddr + kb * 32, v);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tmem_ld8(lane_taddr + ra * 256u + (kb0 + i) * 32 + grp * 8, v + 8 * i);
                 tmem_wait_ld();
-                uint8_t *dst = sA + kb * (T2_ROWS * 128) + row_off;
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    float o[4];
+                for (int i = 0; i < 4; ++i) {
+                    const int kb = kb0 + i;
+                    uint8_t *dst = sA + kb * (T2_ROWS * 128) + row_off;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        o[j] = to_tf32(fmaxf(__uint_as_float(v[c4 * 4 + j]) + b2s[kb * 32 + c4 * 4 + j], 0.f));
-                    *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+                    for (int u = 0; u < 2; ++u) {
+                        const int c4 = 2 * grp + u;
+                        const float4 b = *(const float4 *)(b2s + kb * 32 + c4 * 4);
+                        *(float4 *)(dst + ((c4 ^ rx) << 4)) =
+                            make_float4(to_tf32(fmaxf(__uint_as_float(v[8 * i + 4 * u + 0]) + b.x, 0.f)),
+                                        to_tf32(fmaxf(__uint_as_float(v[8 * i + 4 * u + 1]) + b.y, 0.f)),
+                                        to_tf32(fmaxf(__uint_as_float(v[8 * i + 4 * u + 2]) + b.z, 0.f)),
+                                        to_tf32(fmaxf(__uint_as_float(v[8 * i + 4 * u + 3]) + b.w, 0.f)));
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_all();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&a2_ready[kb], 0);
                 }
-                tc_fence_before();
-                fence_proxy_async_all();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&a2_ready[kb], 0);
             }
             // ---- epilogue 3: layer 3 is computed TRANSPOSED (D3^T = W3 * A2^T): TMEM lane = output channel
             //      (this CTA owns channels [128*rank, 128*rank+128) of the 256-wide chunk), TMEM column = row
-            //      (columns [0,128) = tile of rank 0, [128,256) = tile of rank 1).  Warp (q,h) drains channels
-            //      32q.. for the 128 rows of tile h: a thread holds 32 consecutive rows of ITS channel, the
-            //      section max is a register-only running max (carried across the four 32-row groups), the
-            //      section ends are warp-uniform, and lanes = consecutive channels -> coalesced atomics.
+            //      (columns [0,128) = tile of rank 0, [128,256) = tile of rank 1).  Warp (q,h,g) drains channels
+            //      32q.. for rows [64g, 64g+64) of tile h: a thread holds 32 consecutive rows of ITS channel, the
+            //      section max is a register-only running max (carried across the two 32-row groups; a section that
+            //      crosses row 64 is finished by two atomics), the section ends are warp-uniform, and lanes =
+            //      consecutive channels -> coalesced atomics.
             if (dbgc) dc[4] = clock64();
-            const int4 tdt = ((uint32_t)h == rank) ? td : tdp;
             const int nrows_t = tdt.z;
             int *feat = (int *)(p.out + (size_t)tdt.x * p.feat_pitch * p.ld_feat);
             const int *sect_t = sect_s + h * T2_ROWS;
             for (int nc = 0; nc < Cfg::NCH3; ++nc) {
-                const uint32_t dcol = nc == 0 ? 256u : 0u;
+                const uint32_t reg = nc == 0 ? rb : ra;
+                if (nc == Cfg::NCH3 - 1 && it + 1 < my_pairs) {
+                    // layer 1 of the NEXT pair refills the operand buffer K block by K block behind the last chunk's
+                    // MMAs; its layer-2 MMAs (into the other TMEM region) then run under the drain below
+                    stage_and_layer1(it + 1, true);
+                    if (dbgc) dc[9] = clock64();
+                }
                 mbar_wait(&acc3_full[nc], par);
                 if (dbgc) dc[5 + 2 * nc] = clock64();
                 tc_fence_after();
@@ -343,26 +384,28 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 const float bias = b3s[c];
                 float run = -INFINITY;
 #pragma unroll 1
-                for (int part = 0; part < 4; ++part) {
+                for (int part = 2 * g; part < 2 * g + 2; ++part) {
                     const int g0 = part * 32;
                     uint32_t v[32];
-                    tmem_ld32(lane_taddr + dcol + h * T2_ROWS + g0, v);
+                    tmem_ld32(lane_taddr + reg * 256u + h * T2_ROWS + g0, v);
                     const int rg = g0 + lane;
                     const int sg = sect_t[rg], sn = sect_t[(rg + 1) & (T2_ROWS - 1)];
                     const unsigned em = __ballot_sync(
-                        0xffffffffu, rg < nrows_t && (rg == T2_ROWS - 1 || rg + 1 >= nrows_t || sn != sg));
+                        0xffffffffu, rg < nrows_t && (rg == 64 * g + 63 || rg + 1 >= nrows_t || sn != sg));
                     tmem_wait_ld();
-                    section_max32<(C1 <= 128)>(v, em, run, [&](float m, int end) {
+                    if (dbgc && nc == 0) dc[10 + 2 * (part & 1)] = clock64();
+                    section_max32_blocks(v, em, run, [&](float m, int end) {
                         const float o = to_tf32(m + bias);
                         if (o > 0.f)
                             atomicMax(feat + (size_t)sect_t[g0 + end] * p.ld_feat + c, __float_as_int(o));
                     });
+                    if (dbgc && nc == 0) dc[11 + 2 * (part & 1)] = clock64();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (dbgc) dc[6 + 2 * nc] = clock64();
-                // region drained: chunk 0 frees R1, chunk 1 frees R0 (both waited for by the leader's MMA warp)
-                if (lane == 0) mbar_arrive_cluster(&r_empty[nc == 0 ? 1 : 0], 0);
+                // region drained (waited for by the leader's MMA warp before it is written again)
+                if (lane == 0) mbar_arrive_cluster(&r_empty[reg], 0);
             }
         }
     }

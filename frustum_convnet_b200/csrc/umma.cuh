@@ -127,6 +127,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 // ------------------------------------------------------------------ descriptors
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024>>4 |
@@ -219,6 +227,32 @@ __device__ __forceinline__ void section_max32(const uint32_t (&v)[32], unsigned 
 #pragma unroll
         for (int r = 0; r < 32; ++r)
             if ((mask >> r) & 1u) run = fmaxf(run, __uint_as_float(v[r]));
+    }
+}
+
+// Same contract as section_max32, organised for FEW instructions (the 16-warp epilogue of pointnet_tc2 is issue-bound):
+// 8-row blocks without a section end take a 4+2+1+1 max tree; only blocks that contain an end walk their rows.
+template <typename Emit>
+__device__ __forceinline__ void section_max32_blocks(const uint32_t (&v)[32], unsigned em, float &run, Emit emit) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const unsigned e8 = (em >> (8 * b)) & 0xffu;
+        if (e8 == 0) {                                   // warp-uniform
+            const float m0 = fmaxf(__uint_as_float(v[8 * b + 0]), __uint_as_float(v[8 * b + 1]));
+            const float m1 = fmaxf(__uint_as_float(v[8 * b + 2]), __uint_as_float(v[8 * b + 3]));
+            const float m2 = fmaxf(__uint_as_float(v[8 * b + 4]), __uint_as_float(v[8 * b + 5]));
+            const float m3 = fmaxf(__uint_as_float(v[8 * b + 6]), __uint_as_float(v[8 * b + 7]));
+            run = fmaxf(run, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                run = fmaxf(run, __uint_as_float(v[8 * b + r]));
+                if ((e8 >> r) & 1u) {
+                    emit(run, 8 * b + r);
+                    run = -INFINITY;
+                }
+            }
+        }
     }
 }
 

@@ -104,6 +104,7 @@ class FrustumEngine:
         # 2-CTA (cta_group::2) PointNet kernel for the 256-channel scale(s): measured 57.5 -> 44.6 us on
         # pointnet_s4; no gain at 128 channels (26.2 vs 27.0 us), so those stay on the 1-CTA kernel
         self.pn_cluster = os.environ.get("FCN_PN_CLUSTER", "1") == "1"
+        self.pn_cluster_min = int(os.environ.get("FCN_PN_CLUSTER_MIN", "128"))    # narrowest layer-1 width on the 2-CTA kernel
         self.group_scan = os.environ.get("FCN_GROUP_SCAN") is not None   # A/B: section-scan grouping kernels
         # persistent FCN kernel (all conv layers + heads + decode in one launch, csrc/fcn_mega.cu); FCN_MEGA=0
         # falls back to one fcn_conv_gemm launch per layer + fcn_decode_eval (kept as the A/B and module-API path)
@@ -153,7 +154,7 @@ class FrustumEngine:
                 lay["b%d" % j] = sh.to(f32).contiguous().to(dev)
                 if self.precision == 1 and j >= 2:
                     lay["w%d_tc" % j] = pack_sw128(wf, min(c2, 128) if j == 2 else 128).to(dev)
-                    if self.pn_cluster and c1 >= 256:    # 2-CTA variant: one C2-wide / 256-wide tile per K block
+                    if self.pn_cluster and c1 >= self.pn_cluster_min:    # 2-CTA variant: one C2-wide / 256-wide tile per K block
                         lay["w%d_tc2" % j] = pack_sw128(wf, c2 if j == 2 else 256).to(dev)
             self.pn.append(lay)
         S, V = self.arch.num_scales, self.num_vec

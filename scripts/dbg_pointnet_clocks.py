@@ -38,6 +38,13 @@ print("precision", a.precision)
 print("MMA warp per job: start | wait_a  wait_w  issue")
 for j, r in enumerate(jobs[:56]):
     print("%3d %8d | %6d %6d %6d" % (j, r[0] - base, r[1] - r[0], r[2] - r[1], r[3] - r[2]))
+nj = 24 if a.precision == 2 and scale == 3 else 0
+for it in range(len(jobs) // nj if nj else 0):
+    blk = jobs[it * nj:(it + 1) * nj]
+    seg = lambda lo, hi: (blk[hi - 1, 3] - blk[lo, 0], int((blk[lo:hi, 1] - blk[lo:hi, 0]).sum()), int((blk[lo:hi, 2] - blk[lo:hi, 1]).sum()), int((blk[lo:hi, 3] - blk[lo:hi, 2]).sum()))
+    print("pair %d: start %d span %d | L2 span/wait_a/wait_w/issue %s | c0 %s | c1 %s | gap to next %d" % (
+        it, blk[0, 0] - base, blk[-1, 3] - blk[0, 0], seg(0, 8), seg(8, 16), seg(16, 24),
+        (jobs[(it + 1) * nj, 0] - blk[-1, 3]) if (it + 1) * nj < len(jobs) else -1))
 print("compute warp 0 per tile: start recs_ready | L1_done->acc2wait acc2_ready epi2_done | chunk: acc3_ready epi3_done ...")
 for r in tiles:
     print(" ".join("%8d" % (x - base if x > 0 else -1) for x in r[:16]))
