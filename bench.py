@@ -748,7 +748,9 @@ def main():
     # workload - so that several forwards overlap; its wall time alone would overstate its share 6x)
     sm_total = torch.cuda.get_device_properties(dev).multi_processor_count
     for k in kt["kernels"]:
-        k["sm_fraction"] = min(1.0, plan.mega_grid / sm_total) if k["name"] == "fcn_mega" else 1.0
+        if k["name"] == "fcn_mega":
+            k["sms"] = min(sm_total, plan.mega_grid)
+        k["sm_fraction"] = min(1.0, k.get("sms", sm_total) / sm_total)   # PointNet: clusters/CTAs of its balanced rounds
         k["sm_ms"] = k["ms"] * k["sm_fraction"]
     dom = max(kt["kernels"], key=lambda k: k["sm_ms"])
     traffic = None
@@ -769,6 +771,14 @@ def main():
         "nominal_gflop_per_launch": dom["nominal_gflop"], "traffic": traffic,
         "precision": "tf32-tcgen05" if args.precision == 1 else "fp32-simt",
     }
+    # every tensor-core kernel of the step, same definitions (the two largest SM-time shares are close: see both)
+    roofline["kernels"] = {
+        k["name"]: {"ms_per_launch": round(k["ms"], 5), "sms": k.get("sms", sm_total),
+                    "sm_time_share": round(k["sm_ms"] / sum(x["sm_ms"] for x in kt["kernels"]), 3),
+                    "achieved_tflops": round(k["executed_tflops"], 1),
+                    "frac": round(k["executed_tflops"] / (tf32_peak * k["sm_fraction"]), 3),
+                    "frac_of_whole_gpu": round(k["executed_tflops"] / tf32_peak, 3)}
+        for k in kt["kernels"] if k["executed_gflop"] > 0}
     hbm = {"achieved": value * algo["bytes"] / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
            "frac": value * algo["bytes"] / 1e9 / peaks["hbm_gbs"],
            "algorithmic_bytes_per_frustum": algo["bytes"],

@@ -295,23 +295,34 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
             const float4 rec = recs[row];
             // every warp computes ITS 8 channels (two 16-byte units) of every K block, in the order the MMAs consume
             // them: a K block is complete ~1/4 of a block time after its buffer slice is free
-            for (int kb = 0; kb < Cfg::KB1; ++kb) {
-                if (chase) mbar_wait(&a_free[kb], (it & 1) ^ 1);
-                uint8_t *dst = sA + kb * (T2_ROWS * 128) + row_off;
+            // (two K blocks per publication.  Measured: the cost of a publication hardly depends on how the loads, FMAs
+            // and the proxy fence are arranged - the 128 KB of A1 stores compete with the MMA operand reads and the
+            // weight fills for the SM's shared-memory data path, which this kernel keeps ~90 % busy)
+            long long *dl = p.dbg_clocks + 6144 + 32 * it;
+            if (dbgc) dl[0] = clock64();
+#pragma unroll 1
+            for (int kb0 = 0; kb0 < Cfg::KB1; kb0 += 2) {
+                if (chase) mbar_wait(&a_free[kb0 + 1], (it & 1) ^ 1);     // in-order MMAs: implies a_free[kb0]
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int c4 = 2 * grp + u;
-                    float o[4];
+                for (int i = 0; i < 2; ++i) {
+                    const int kb = kb0 + i;
+                    uint8_t *dst = sA + kb * (T2_ROWS * 128) + row_off;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 w = w1s[kb * 32 + c4 * 4 + j];
-                        o[j] = to_tf32(fmaxf(fmaf(rec.z, w.z, fmaf(rec.y, w.y, fmaf(rec.x, w.x, w.w))), 0.f));
+                    for (int u = 0; u < 2; ++u) {
+                        const int c4 = 2 * grp + u;
+                        float o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 w = w1s[kb * 32 + c4 * 4 + j];
+                            o[j] = to_tf32(fmaxf(fmaf(rec.z, w.z, fmaf(rec.y, w.y, fmaf(rec.x, w.x, w.w))), 0.f));
+                        }
+                        *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                    *(float4 *)(dst + ((c4 ^ rx) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
                 }
                 fence_proxy_async_all();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&a1_ready[kb], 0);
+                if (lane < 2) mbar_arrive_cluster(&a1_ready[kb0 + lane], 0);
+                if (dbgc) dl[1 + (kb0 >> 1)] = clock64();
             }
         };
         stage_and_layer1(0, false);
@@ -352,10 +363,12 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                                         to_tf32(fmaxf(__uint_as_float(v[8 * i + 4 * u + 2]) + b.z, 0.f)),
                                         to_tf32(fmaxf(__uint_as_float(v[8 * i + 4 * u + 3]) + b.w, 0.f)));
                     }
-                    tc_fence_before();
-                    fence_proxy_async_all();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&a2_ready[kb], 0);
+                    if (i & 1) {                 // publish two K blocks per proxy fence
+                        tc_fence_before();
+                        fence_proxy_async_all();
+                        __syncwarp();
+                        if (lane < 2) mbar_arrive_cluster(&a2_ready[kb - 1 + lane], 0);
+                    }
                 }
             }
             // ---- epilogue 3: layer 3 is computed TRANSPOSED (D3^T = W3 * A2^T): TMEM lane = output channel

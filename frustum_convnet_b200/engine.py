@@ -797,10 +797,26 @@ class _Plan:
         rows_exec = [int(c.sum().item()) for c in self.cnt]
         rows_nom = [self.B * self.T[s] * eng.arch.nsample[s] for s in range(S)]
         kern = [dict(name="group_rows", ms=float(acc[0]), executed_gflop=0.0, nominal_gflop=0.0)]
+        sm = torch.cuda.get_device_properties(eng.device).multi_processor_count
+        ntiles = self.ntiles.cpu().tolist()
+
+        def balanced(n, slots):          # csrc/umma.cuh balanced_stride
+            rounds = -(-n // slots)
+            return -(-n // rounds) if n > 0 else 0
+
         for s in range(S):
             c1, c2, c3 = eng.arch.mlps[s]
             mac = 3 * c1 + c1 * c2 + c2 * c3
-            kern.append(dict(name="pointnet_s%d" % (s + 1), ms=float(acc[1 + s]),
+            a = self.pn_args[s]
+            nt = min(int(ntiles[s]), int(a.max_tiles))
+            if a.precision == 2:         # 2-CTA clusters, one tile pair per cluster and round
+                sms = 2 * balanced((nt + 1) // 2, (sm & ~1) // 2)
+            elif a.precision == 1:       # persistent 1-CTA kernel, two CTAs per SM at <= 64 channels
+                per_sm = 2 if c1 <= 64 else 1
+                sms = min(sm, -(-balanced(nt, sm * per_sm) // per_sm))
+            else:
+                sms = sm
+            kern.append(dict(name="pointnet_s%d" % (s + 1), ms=float(acc[1 + s]), sms=int(sms), tiles=nt,
                              executed_gflop=2e-9 * mac * rows_exec[s], nominal_gflop=2e-9 * mac * rows_nom[s]))
         fcn_gf = []
         for j, (L, a) in enumerate(zip(eng.layers, self.conv_args)):

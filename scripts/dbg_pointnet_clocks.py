@@ -30,7 +30,8 @@ t = buf.cpu().numpy()
 a.dbg_clocks = None
 jobs = t[:4000].reshape(-1, 4)
 jobs = jobs[jobs[:, 0] > 0]
-tiles = t[4096:].reshape(-1, 16)
+l1 = t[6144:6144+32*8].reshape(-1, 32)
+tiles = t[4096:6144].reshape(-1, 16)
 tiles = tiles[tiles[:, 0] > 0]
 base = min(jobs[0, 0], tiles[0, 0])
 print("scale", scale + 1, "jobs", len(jobs), "tiles(CTA0)", len(tiles))
@@ -48,3 +49,7 @@ for it in range(len(jobs) // nj if nj else 0):
 print("compute warp 0 per tile: start recs_ready | L1_done->acc2wait acc2_ready epi2_done | chunk: acc3_ready epi3_done ...")
 for r in tiles:
     print(" ".join("%8d" % (x - base if x > 0 else -1) for x in r[:16]))
+print("layer-1 stamps (warp 0): start | per K block: arrive, next a_free passed")
+for r in l1:
+    if r[0] > 0:
+        print(" ".join("%7d" % (x - base if x > 0 else -1) for x in r[:17]))
