@@ -463,7 +463,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.5,
                     help="device time to accumulate per mode by repeating the K-step region (median reported)")
     ap.add_argument("--max-regions", type=int, default=400)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "8")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("FCN_STREAMS", "10")),
                     help="forwards in flight: steps are issued round-robin on this many CUDA streams")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
