@@ -383,9 +383,10 @@ def run_train(args, rank, local_rank, world):
         ev[4].record()
         torch.cuda.synchronize()
         acc += [ev[j].elapsed_time(ev[j + 1]) for j in range(4)]
-    phases = {"forward_ms": acc[0] / 20, "losses_graph_ms": acc[1] / 20, "backward_ms": acc[2] / 20,
-              "adam_ms": acc[3] / 20,
-              "note": "one step at a time on one stream (CUDA events); losses = PyTorch ops replayed as one CUDA graph"}
+    phases = {"forward_ms": acc[0] / 20, "losses_ms": acc[1] / 20, "backward_ms": acc[2] / 20,
+              "adam_ms": acc[3] / 20, "loss_impl": ts.loss_impl,
+              "note": "one step at a time on one stream (CUDA events); losses = fcn_det_loss (losses + dlogits + "
+                      "metrics in one call) when loss_impl == 'kernel'"}
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     ref_model = build()

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 P1=$((29700 + RANDOM % 100)); P2=$((29850 + RANDOM % 100)); P3=$((29400 + RANDOM % 100))
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P1 \
     bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_eval.json 2> gpurun_out/bench_${TAG}_eval.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P2 \
+[ "$3" = "skip-nccl" ] || timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P2 \
     bench.py --gpus $N --steps 20 --warmup 5 --exchange nccl > gpurun_out/bench_${TAG}_eval_nccl.json 2> gpurun_out/bench_${TAG}_eval_nccl.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P3 \
     bench.py --gpus $N --train --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_train.json 2> gpurun_out/bench_${TAG}_train.err
@@ -20,4 +20,4 @@ for n in ("eval", "eval_nccl", "train"):
     except Exception as e:
         print(n, "failed", e)
 PY
-tail -2 gpurun_out/bench_${TAG}_eval.err gpurun_out/bench_${TAG}_train.err
+tail -qn 2 gpurun_out/bench_${TAG}_eval.err gpurun_out/bench_${TAG}_train.err
