@@ -88,7 +88,7 @@ class MegaLayer(C.Structure):
         ("relu", C.c_int), ("round_out", C.c_int), ("up", C.c_int), ("Cout", C.c_int),
         ("P_m", C.c_int), ("T_out", C.c_int), ("n_rows", C.c_int),
         ("ld_out", C.c_int), ("P_store", C.c_int), ("T_store", C.c_int), ("c_off", C.c_int),
-        ("is_heads", C.c_int), ("flag_base", C.c_int), ("out_map", C.c_int), ("reserved0", C.c_int),
+        ("is_heads", C.c_int), ("flag_base", C.c_int), ("out_map", C.c_int), ("k_atoms", C.c_int),
         ("w_tc", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
     ]
 

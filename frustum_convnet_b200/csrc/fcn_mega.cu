@@ -38,14 +38,14 @@ using namespace umma;
 
 constexpr int MG_ROWS = 128;
 constexpr int MG_THREADS = 6 * 32;   // warp 0: scheduler + TMA producer, warp 1: MMA, warps 2-5: epilogue
-constexpr int MG_NSTAGE = 3;         // 64-wide K stages: 2 x 16 KB of A + 32 KB of W each
+constexpr int MG_NSTAGE = 3;         // stage slot: 2 x 16 KB of A + 32 KB of W (NT <= 128: 64-wide K; NT = 256: 32-wide)
 constexpr int MG_A_ATOM = MG_ROWS * 128, MG_A_STAGE = 2 * MG_A_ATOM;
-constexpr int MG_W_STAGE = 2 * 128 * 128;                     // sized for NT = 128
+constexpr int MG_W_STAGE = 2 * 128 * 128;                     // two [128 x 32] atoms or one [256 x 32] atom
 constexpr int MG_OFF_W = MG_NSTAGE * MG_A_STAGE;
 constexpr int MG_OFF_STG = MG_OFF_W + MG_NSTAGE * MG_W_STAGE; // epilogue staging: 4 warps x 2 x [32 rows x 128 B]
 constexpr int MG_STG_BYTES = 4 * 2 * 4096;
-constexpr int MG_OFF_BIAS = MG_OFF_STG + MG_STG_BYTES;        // float bias[2][128] (per job parity)
-constexpr int MG_OFF_BAR = MG_OFF_BIAS + 2 * 128 * 4;
+constexpr int MG_OFF_BIAS = MG_OFF_STG + MG_STG_BYTES;        // float bias[256] of the current job's N tile
+constexpr int MG_OFF_BAR = MG_OFF_BIAS + 256 * 4;
 constexpr int MG_JOBQ = 4;                                    // job descriptors in flight inside a CTA
 constexpr int MG_NBAR = 2 * MG_NSTAGE + 4 + 2 * MG_JOBQ;      // full/empty, acc_full/acc_empty [2], job_full/job_empty
 constexpr int MG_OFF_JOBQ = MG_OFF_BAR + MG_NBAR * 8;         // fcn_mega_job[MG_JOBQ] (64 B each)
@@ -122,7 +122,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
         for (int i = 0; i < MG_JOBQ; ++i) { mbar_init(&job_full[i], 1); mbar_init(&job_empty[i], 5); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    if (warp == 1) tmem_alloc<512>(tmem_slot);    // two accumulators of up to 256 columns
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -165,7 +165,9 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
                 if (dbg) { dbg[0] = clock64(); dbg[1] = jcur; }
                 const int r0 = job.m_tile * MG_ROWS;
                 const int NS = L.n_stage;
-                const uint32_t w_bytes = (uint32_t)L.NT * 256u;          // [NT rows x 64 tf32] per stage
+                const int ka = L.k_atoms == 1 ? 1 : 2;                   // 32-wide K atoms per stage
+                const uint32_t w_bytes = (uint32_t)(L.NT * 128 * ka);    // [NT rows x 32 tf32] per atom
+                const uint32_t a_bytes = (uint32_t)(ka * MG_A_ATOM);
                 const uint8_t *wsrc = (const uint8_t *)L.w_tc + (size_t)job.n_tile * NS * w_bytes;
                 // weights do not depend on other tiles: the first ring-full of weight stages streams WHILE this
                 // tile's dependencies are awaited (only the A boxes wait for the producer tiles).  (Issuing every
@@ -174,7 +176,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
                 for (int s = 0; s < npre; ++s) {
                     const uint32_t sg = stage + s, st = sg % MG_NSTAGE, ph = (sg / MG_NSTAGE) & 1;
                     mbar_wait(&empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[st], MG_A_STAGE + w_bytes);
+                    mbar_arrive_expect_tx(&full[st], a_bytes + w_bytes);
                     bulk_g2s(sW + st * MG_W_STAGE, wsrc + (size_t)s * w_bytes, w_bytes, &full[st]);
                 }
                 const int jnext = atomicAdd(job_counter, 1);   // in flight during the dependency wait below
@@ -199,11 +201,10 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
                     if (s == npre) next_layer = publish(q + 1, jnext);   // first ring-full issued: fetch the next job
                     if (s >= npre) {
                         mbar_wait(&empty[st], ph ^ 1);
-                        mbar_arrive_expect_tx(&full[st], MG_A_STAGE + w_bytes);
+                        mbar_arrive_expect_tx(&full[st], a_bytes + w_bytes);
                         bulk_g2s(sW + st * MG_W_STAGE, wsrc + (size_t)s * w_bytes, w_bytes, &full[st]);
                     }
-#pragma unroll
-                    for (int a = 0; a < 2; ++a) {
+                    for (int a = 0; a < ka; ++a) {
                         const uint32_t dst = smem_u32(sA) + st * MG_A_STAGE + a * MG_A_ATOM;
                         if (seg < L.n_seg) {
                             const fcn_mega_seg &sgm = L.seg[seg];
@@ -233,7 +234,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
             if (lane == 0) mbar_arrive(&job_empty[slot]);
             if (layer < 0) break;
             const fcn_mega_layer &L = s_layers[layer];
-            const int NS = L.n_stage, NT = L.NT;
+            const int NS = L.n_stage, NT = L.NT, ka = L.k_atoms == 1 ? 1 : 2;
             const uint32_t idesc = make_idesc_tf32(128, NT);
             const uint32_t w_atom16 = (uint32_t)(NT * 128) >> 4;          // second 32-wide K atom of a W stage
             const uint32_t buf = q & 1;
@@ -242,7 +243,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
             mbar_wait(&acc_empty[buf], ((q >> 1) & 1) ^ 1);               // epilogue of job q-2 drained this buffer
             if (dbg) dbg[6] = clock64();
             tc_fence_after();
-            const uint32_t dtmem = tmem_base + buf * 128;
+            const uint32_t dtmem = tmem_base + buf * 256;
             for (int s = 0; s < NS; ++s, ++stage) {
                 const uint32_t st = stage % MG_NSTAGE, ph = (stage / MG_NSTAGE) & 1;
                 mbar_wait(&full[st], ph);
@@ -251,8 +252,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
                 if (mg_elect_one()) {
                     const uint64_t ad = adesc0 + (uint64_t)(st * (MG_A_STAGE >> 4));
                     const uint64_t bd = bdesc0 + (uint64_t)(st * (MG_W_STAGE >> 4));
-#pragma unroll
-                    for (int a = 0; a < 2; ++a)
+                    for (int a = 0; a < ka; ++a)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             mma_tf32(dtmem, ad + (uint64_t)(a * (MG_A_ATOM >> 4) + 2 * k),
@@ -290,9 +290,11 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
             const fcn_mega_layer &L = s_layers[layer];
             const int NT = L.NT;
             const uint32_t buf = q & 1;
-            // bias of this N tile -> shared memory while the K loop still runs (L1 is invalidated by the fences)
-            float *bs = sbias + buf * 128;
-            if (etid < NT) bs[etid] = __ldg(L.bias + n_tile * NT + etid);
+            // bias of this N tile -> shared memory while the K loop still runs (L1 is invalidated by the fences);
+            // one buffer: the first barrier says "every warp is done with the previous job's bias"
+            float *bs = sbias;
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            for (int i = etid; i < NT; i += 128) bs[i] = __ldg(L.bias + n_tile * NT + i);
             asm volatile("bar.sync 1, 128;\n" ::: "memory");
             const int r = m_tile * MG_ROWS + qd * 32 + lane;        // flattened GEMM row of this thread
             const int b = r / L.P_m, rt = r - b * L.P_m;            // (frustum, position)
@@ -302,7 +304,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
             mbar_wait(&acc_full[buf], (q >> 1) & 1);
             if (dbg) dbg[11] = clock64();
             tc_fence_after();
-            const uint32_t lane_taddr = tmem_base + buf * 128 + ((uint32_t)(qd * 32) << 16);
+            const uint32_t lane_taddr = tmem_base + buf * 256 + ((uint32_t)(qd * 32) << 16);
             if (!L.is_heads) {
                 // one 32-column chunk: registers -> +bias/ReLU/TF32 -> swizzled staging tile -> TMA store
                 auto emit_chunk = [&](const uint32_t (&v)[32], int c0) {
@@ -425,7 +427,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
     // self-cleaning: the last CTA out resets the scheduler state for the next forward and, on the multi-GPU
     // path, raises this rank's epoch flag in every peer (all result rows were fenced at system scope above)

@@ -116,6 +116,12 @@ class FrustumEngine:
         # 0 = adaptive: 2/3 of the smallest per-layer tile count of the main chain, within [4, 48] (car B=32: 24,
         # people: 48, SUN-RGBD: 6 - measured optima 24 / 32-48 / 6-8)
         self.mega_grid = int(os.environ.get("FCN_MEGA_GRID", "0"))
+        # 256-wide N tiles for the layers with >= 256 output columns: 25 % less shared-memory traffic per MAC
+        # (the A box feeds twice as many MMA columns) but half as many jobs per layer.  Measured
+        # (B=32): people +6.5 % (200-step regions) / +1.6 % (20-step), car and SUN-RGBD +-0.5 %.  "auto" uses
+        # them when every main-chain layer still has >= 24 tiles (people, car at B >= 64); True / False force.
+        v = os.environ.get("FCN_MEGA_NT256", "auto")
+        self.mega_nt256 = "auto" if v == "auto" else (v == "1")
         self.tile_rows = 64 if self.precision == 0 else 128
         self.out_size = reg_out_size(dataset, self.num_bins)
         self.ld_logit = _round_up(2 + self.out_size, 64)
@@ -437,18 +443,29 @@ class _Plan:
     def mega_descs(self):
         """Shape-level layer descriptions for the persistent FCN kernel (pure host arithmetic, testable on the CPU)."""
         eng = self.eng
-        descs = []
-        for L in eng.layers:
-            src0, stride = L.segs[0][0], L.segs[0][3]
-            T_in, P_in = self.valid_T[src0], self.buf[src0].shape[1]
-            T_out = T_in if stride == 1 else (T_in + 1) // 2
-            P_m = P_in // stride
-            out = self.buf[L.out]
-            nt = 128 if L.n_cols % 128 == 0 else 64
-            descs.append(_mega.LayerDesc(L.name, L.segs, L.K_pad, L.n_cols, L.Cout, L.up, L.relu, L.out, L.c_off, nt,
-                                         1 if L.name != "heads" else 0, P_m, T_out, self.B * P_m, out.shape[2],
-                                         out.shape[1], self.valid_T[L.out]))
-        return descs
+
+        def build(wide):
+            descs = []
+            for L in eng.layers:
+                src0, stride = L.segs[0][0], L.segs[0][3]
+                T_in, P_in = self.valid_T[src0], self.buf[src0].shape[1]
+                T_out = T_in if stride == 1 else (T_in + 1) // 2
+                P_m = P_in // stride
+                out = self.buf[L.out]
+                nt = 128 if L.n_cols % 128 == 0 else 64
+                if wide and L.n_cols % 256 == 0 and L.name != "heads":
+                    nt = 256
+                descs.append(_mega.LayerDesc(L.name, L.segs, L.K_pad, L.n_cols, L.Cout, L.up, L.relu, L.out, L.c_off, nt,
+                                             1 if L.name != "heads" else 0, P_m, T_out, self.B * P_m, out.shape[2],
+                                             out.shape[1], self.valid_T[L.out]))
+            return descs
+
+        if eng.mega_nt256 == "auto":
+            descs = build(True)
+            if min(d.m_tiles * d.n_tiles for d in descs if not d.name.endswith("_deconv") and d.name != "heads") >= 24:
+                return descs
+            return build(False)
+        return build(bool(eng.mega_nt256))
 
     def _build_mega(self):
         """Tables of the persistent FCN kernel (mega.py): tensor maps, layers, topologically ordered jobs."""
@@ -464,7 +481,7 @@ class _Plan:
             else:                   # epilogue stores: one tensor row = `par` (= up) consecutive output rows
                 _lib.call("fcn_encode_store_map", C.addressof(maps) + 128 * i, _ptr(t), self.B * t.shape[1] // par,
                           par * t.shape[2])
-        ptrs = [(a.w_tc, a.bias, a.out) for a in self.conv_args]
+        ptrs = [(_ptr(L.tc_image(d.NT)), a.bias, a.out) for L, d, a in zip(eng.layers, descs, self.conv_args)]
         LA, JA = _mega.to_ctypes(descs, rows, jobs, ptrs)
         self._mega_host = (maps, LA)                   # HOST tables (copied into the kernel parameters per launch)
         self._mega_dev = torch.frombuffer(bytearray(bytes(JA)), dtype=torch.uint8).to(dev)

@@ -3,7 +3,7 @@
 Turns the engine's per-layer GEMM descriptions (``_ConvLayer`` + the plan's buffers) into
   * one tensor map per distinct (source map, conv stride),
   * a layer table (``fcn_mega_layer``),
-  * a job table (``fcn_mega_job``): one [128 rows x NT columns] output tile each, in TOPOLOGICAL order, with the
+  * a job table (``fcn_mega_job``): one [128 rows x NT columns] output tile each (NT = 256 | 128 | 64), in TOPOLOGICAL order, with the
     completion counters of the producer tiles it reads.
 The order interleaves the side transposed convs with the next block's first layer, so CTAs that would wait on
 a dependency find independent work first.  Replaces the launch sequence of ConvFeatNet.forward + heads + decode
@@ -34,6 +34,7 @@ class LayerDesc:
         self.ld_out, self.P_store, self.T_store = ld_out, P_store, T_store
         self.m_tiles = (n_rows + ROWS - 1) // ROWS
         self.n_tiles = n_cols // NT
+        self.k_atoms = 1 if NT == 256 else 2       # 32-wide K atoms per shared-memory stage (stage = 64 KB at most)
 
 
 def job_order(layers: Sequence[LayerDesc]) -> List[int]:
@@ -151,7 +152,7 @@ def to_ctypes(layers: Sequence[LayerDesc], rows, jobs, ptrs):
         for j, sg in enumerate(row["segs"]):
             a.seg[j].map_idx, a.seg[j].kblocks, a.seg[j].tap, a.seg[j].stride = (sg["map_idx"], sg["kblocks"],
                                                                                   sg["tap"], sg["stride"])
-        a.n_stage, a.NT, a.n_tiles_n = L.K_pad // 64, L.NT, L.n_tiles
+        a.n_stage, a.NT, a.n_tiles_n, a.k_atoms = L.K_pad // (32 * L.k_atoms), L.NT, L.n_tiles, L.k_atoms
         a.relu, a.round_out, a.up, a.Cout = L.relu, L.round_out, L.up, L.Cout
         a.P_m, a.T_out, a.n_rows = L.P_m, L.T_out, L.n_rows
         a.ld_out, a.P_store, a.T_store, a.c_off = L.ld_out, L.P_store, L.T_store, L.c_off

@@ -208,13 +208,14 @@ typedef struct {
 typedef struct {
     int n_seg;
     fcn_mega_seg seg[FCN_MAX_SEGS];
-    int n_stage;                 /* K_pad / 64 */
-    int NT, n_tiles_n;           /* N tile (128 | 64) and their number */
+    int n_stage;                 /* K stages per tile: K_pad / (32 * k_atoms) */
+    int NT, n_tiles_n;           /* N tile (256 | 128 | 64) and their number */
     int relu, round_out, up, Cout;
     int P_m, T_out, n_rows;      /* GEMM row space: row r = b*P_m + t, valid iff t < T_out; n_rows = B*P_m */
     int ld_out, P_store, T_store, c_off;
     int is_heads, flag_base;
-    int out_map, reserved0;      /* tensor map of the epilogue's TMA store (fcn_encode_store_map); unused for heads */
+    int out_map;                 /* tensor map of the epilogue's TMA store (fcn_encode_store_map); unused for heads */
+    int k_atoms;                 /* 32-wide K atoms per stage: 2 (NT <= 128) or 1 (NT = 256); 0 reads as 2 */
     const void *w_tc;            /* packed stage images, N-tile major */
     const float *bias;
     float *out;

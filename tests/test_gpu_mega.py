@@ -110,3 +110,23 @@ def test_mega_other_workloads(wl, B, monkeypatch):
     assert torch.equal(r0, r1) and torch.equal(c0, c1)
     for a, b in zip(o0, o1):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("wl,B", [("car", 3), ("people", 2)])
+def test_mega_wide_tiles_bit_exact(wl, B, monkeypatch):
+    """256-wide N tiles (32-wide K stages, two 256-column TMEM accumulators): same K order per output element as the
+    128-wide tiles and the per-layer GEMMs -> bit-identical.  ("auto" picks them for >= 24 tiles per layer.)"""
+    from frustum_convnet_b200 import config, synth
+    cfg, w = config.load_workload(wl)
+    sd = synth.make_state_dict(w["arch"], w["num_vec"], cfg.DATA.DATASET_NAME, seed=11)
+    data = synth.make_frustums(wl, B, seed=5)
+    d = cuda_data(data)
+    shape = _shape(data, w)
+    monkeypatch.setenv("FCN_MEGA_NT256", "0")
+    _, _, o0, c0, r0 = _forward(monkeypatch, False, w, sd, cfg, d, shape=shape)
+    monkeypatch.setenv("FCN_MEGA_NT256", "1")
+    _, p1, o1, c1, r1 = _forward(monkeypatch, True, w, sd, cfg, d, graph=True, shape=shape)
+    assert any(x.NT == 256 for x in p1.mega_descs())
+    assert torch.equal(r0, r1) and torch.equal(c0, c1)
+    for a, b in zip(o0, o1):
+        assert torch.equal(a, b)

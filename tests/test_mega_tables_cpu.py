@@ -14,12 +14,13 @@ from frustum_convnet_b200 import mega
 from frustum_convnet_b200.engine import FrustumEngine, _Plan
 
 
-def _plan(golden_loader, name):
+def _plan(golden_loader, name, nt256=False):
     g, data, sd, w, cfg = golden_loader(name)
     tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
     eng = FrustumEngine(w["arch"], w["num_vec"], cfg.DATA.DATASET_NAME, cfg.DATA.HEIGHT_HALF, 12, tsd, "cpu",
                         precision=1)
     eng.use_tma = False          # no driver here: tensor maps are not encoded, the tables do not need them
+    eng.mega_nt256 = nt256
     B = data["point_cloud"].shape[0]
     T = [data["center_ref%d" % (i + 1)].shape[2] for i in range(w["arch"].num_scales)]
     return eng, _Plan(eng, B, data["point_cloud"].shape[2], tuple(T)), g
@@ -89,9 +90,13 @@ def _execute(eng, plan, feats, seed):
     return buf, len(jobs), len(map_keys)
 
 
-@pytest.mark.parametrize("name,seed", [("car_small_b3", 1), ("people_small_b2", 2), ("sunrgbd_full_b2", 3)])
-def test_job_table_execution_reproduces_reference_fcn(golden_loader, name, seed):
-    eng, plan, g = _plan(golden_loader, name)
+@pytest.mark.parametrize("name,seed,nt256", [("car_small_b3", 1, False), ("people_small_b2", 2, False),
+                                             ("sunrgbd_full_b2", 3, False), ("car_small_b3", 4, True),
+                                             ("sunrgbd_full_b2", 5, True)])
+def test_job_table_execution_reproduces_reference_fcn(golden_loader, name, seed, nt256):
+    eng, plan, g = _plan(golden_loader, name, nt256)
+    if nt256:
+        assert any(d.NT == 256 and d.k_atoms == 1 for d in plan.mega_descs())
     S = eng.arch.num_scales
     feats = [np.transpose(g["feat%d" % (i + 1)], (0, 2, 1)).astype(np.float64) for i in range(S)]
     buf, njobs, nmaps = _execute(eng, plan, feats, seed)
@@ -128,3 +133,19 @@ def test_full_size_car_table_shape():
     heads = [j for j in jobs if descs[j["layer"]].name == "heads"]
     assert len(heads) == 36 and all(len(j["deps"]) == 3 for j in heads)
     assert all(j["deps"] == [] for j in jobs if descs[j["layer"]].name == "block1_conv1")
+
+
+def test_wide_tile_rule_is_by_tile_count():
+    """FCN_MEGA_NT256=auto: 256-wide tiles only when every main-chain layer keeps >= 24 tiles."""
+    from frustum_convnet_b200 import config, synth
+    cfg, w = config.load_workload("car")
+    sd = synth.make_state_dict(w["arch"], w["num_vec"], cfg.DATA.DATASET_NAME, seed=7)
+    tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    eng = FrustumEngine(w["arch"], w["num_vec"], cfg.DATA.DATASET_NAME, cfg.DATA.HEIGHT_HALF, 12, tsd, "cpu", precision=1)
+    eng.use_tma = False
+    eng.mega_nt256 = "auto"
+    small = _Plan(eng, 32, 1024, (280, 140, 70, 35)).mega_descs()
+    big = _Plan(eng, 128, 1024, (280, 140, 70, 35)).mega_descs()
+    assert max(d.NT for d in small) == 128 and max(d.NT for d in big) == 256
+    for d in big:
+        assert d.k_atoms == (1 if d.NT == 256 else 2) and d.K_pad % (32 * d.k_atoms) == 0
