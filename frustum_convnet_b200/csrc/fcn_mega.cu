@@ -407,13 +407,26 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
                         for (int a6 = 0; a6 < 6; ++a6) {
                             const size_t base = (size_t)R_lo * widths[a6];
                             const int nflt = (R_hi - R_lo) * widths[a6];
-                            for (int i = etid; i < nflt; i += 128) {
-                                const float v = loc[a6][base + i];
-                                for (int o = 1; o < p.n_out; ++o) ((float *const *)&p.outs[o])[a6][base + i] = v;
+                            // four independent loads in flight per thread (the rows were just written: L2 latency),
+                            // then the posted remote stores
+#pragma unroll 1
+                            for (int i = etid; i < nflt; i += 512) {
+                                float v[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    v[u] = (i + 128 * u < nflt) ? __ldcg(loc[a6] + base + i + 128 * u) : 0.f;
+                                for (int o = 1; o < p.n_out; ++o) {
+                                    float *dst = ((float *const *)&p.outs[o])[a6] + base + i;
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u)
+                                        if (i + 128 * u < nflt) dst[128 * u] = v[u];
+                                }
                             }
                         }
                     }
-                    __threadfence_system();                // remote (NVLink) stores before the completion count
+                    // no system-scope fence here: nothing consumes a heads tile's counter remotely; every thread
+                    // fences its remote stores ONCE before the CTA reports completion (end of the kernel), and the
+                    // last CTA raises the epoch flags after all CTAs have reported
                 }
                 __threadfence();
                 __syncwarp();
@@ -423,6 +436,7 @@ fcn_mega_kernel(const __grid_constant__ MegaParams P) {
         }
         if (lane == 0) bulk_wait_all();
     }
+    if (p.n_out > 1) __threadfence_system();      // this thread's remote (NVLink) result stores, if any
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
