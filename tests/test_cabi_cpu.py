@@ -105,3 +105,25 @@ def test_public_header_is_plain_c(tmp_path):
     txt = open(os.path.join(ROOT, "include", "frustum_b200.h")).read()
     includes = re.findall(r'#\s*include\s*[<"]([^>"]+)[>"]', txt)
     assert includes and all(i in ("stdint.h", "stddef.h") for i in includes), includes   # no torch / CUDA headers
+
+
+def test_ctypes_mirrors_have_the_size_of_the_c_structs(tmp_path):
+    """frustum_convnet_b200/_lib.py restates every argument struct of include/frustum_b200.h for ctypes: a field
+    added on one side only would silently shift everything behind it.  Compare sizeof() as gcc sees the header."""
+    import ctypes
+    import subprocess
+    from frustum_convnet_b200 import _lib
+    pairs = [("fcn_group_args", _lib.GroupArgs), ("fcn_pointnet_args", _lib.PointnetArgs),
+             ("fcn_conv_seg", _lib.ConvSeg), ("fcn_conv_args", _lib.ConvArgs), ("fcn_decode_out", _lib.DecodeOut),
+             ("fcn_mega_seg", _lib.MegaSeg), ("fcn_mega_layer", _lib.MegaLayer), ("fcn_mega_job", _lib.MegaJob),
+             ("fcn_mega_args", _lib.MegaArgs), ("fcn_train_src", _lib.TrainSrc), ("fcn_train_seg", _lib.TrainSeg),
+             ("fcn_train_layer", _lib.TrainLayer), ("fcn_train_pool_args", _lib.TrainPool),
+             ("fcn_loss_args", _lib.LossArgs), ("fcn_input_args", _lib.InputArgs)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "frustum_b200.h"\nint main(void) {\n' +
+                   "".join('    printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n, _ in pairs) + "    return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, cls in pairs:
+        assert int(sizes[name]) == ctypes.sizeof(cls), (name, sizes[name], ctypes.sizeof(cls))
