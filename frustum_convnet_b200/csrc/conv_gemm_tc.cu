@@ -119,7 +119,6 @@ conv_gemm_tc_kernel(const __grid_constant__ fcn_conv_args p) {
             }
         }
         if (gt_elect_one()) mma_commit(acc_full);
-        pdl_launch_dependents_late();   // K loop issued: let the next layer's prologue start
         __syncwarp();
     } else {
         // ================= A producers, then epilogue =================

@@ -136,7 +136,6 @@ conv_gemm_tma_kernel(const __grid_constant__ ConvTmaParams P) {
             __syncwarp();
         }
         if (gm_elect_one()) mma_commit(acc_full);
-        pdl_launch_dependents_late();   // K loop issued: let the next layer's prologue start
         __syncwarp();
     } else {
         // ================= epilogue: TMEM -> +bias (+ReLU, TF32 rounding) -> position-major store =========

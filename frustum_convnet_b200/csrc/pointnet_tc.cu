@@ -216,7 +216,6 @@ pointnet_tc_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 __syncwarp();
             }
         }
-        pdl_launch_dependents_late();   // all MMAs of this CTA are issued; only the last epilogue remains
     } else {
         // ================= compute / epilogue warps =================
         const int q = warp & 3, h = warp >> 2;

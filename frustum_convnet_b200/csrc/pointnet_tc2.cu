@@ -255,7 +255,6 @@ pointnet_tc2_kernel(const __grid_constant__ fcn_pointnet_args p) {
                 }
             }
         }
-        pdl_launch_dependents_late();   // both CTAs: every MMA of this pair is issued / relayed
     } else {
         // ================= compute / epilogue warps (both CTAs, own 128-row tile) =================
         // warp = q + 4 * grp: q = TMEM lane quadrant (rows 32q.. of the tile / channels 32q.. of the transposed layer 3),
